@@ -1,0 +1,979 @@
+// fastlio_b200.cu — C-ABI implementation (include/fastlio_b200.h): host orchestration of the sm_100a kernels.
+// One CUDA stream per map; all calls on a handle are issued by one caller thread (as the reference does,
+// SURVEY.md §8b "Threading").  No CPU fallback anywhere: without a usable CUDA device every call returns an error.
+#include "../../include/fastlio_b200.h"
+#include "map_kernels.cuh"
+#include "knn_kernels.cuh"
+#include "meas_kernels.cuh"
+#include "esikf_host.hpp"
+
+#include <cub/device/device_scan.cuh>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace flb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess) return set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* flb_last_error(void) { return g_err; }
+extern "C" const char* flb_version(void) { return "fastlio_b200 0.1 (sm_100a)"; }
+extern "C" int flb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static inline uint32_t next_pow2(uint64_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+static inline int grid_for(int n, int threads, int max_blocks) {
+  int g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return g > max_blocks ? max_blocks : g;
+}
+
+// ------------------------------------------------------------------------------------------------ map
+struct flb_map {
+  MapDev d{};
+  flb_map_config cfg{};
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  uint32_t hash_cap = 0, chash_cap = 0;
+  size_t device_bytes = 0;
+  bool has_root = false;
+  int rehash_count = 0;
+  // staging
+  float4* stage = nullptr;       // device float4 staging for host uploads
+  int stage_cap = 0;
+  unsigned char* raw = nullptr;  // device raw strided upload buffer
+  size_t raw_cap = 0;
+  uint64_t* skeys = nullptr;     // scratch hash of the downsampled insert
+  unsigned long long* sbest = nullptr;
+  uint32_t scratch_cap = 0;
+  float* dparams = nullptr;      // small device parameter buffer (boxes / points)
+  int dparams_cap = 0;
+  float4* outbuf = nullptr;      // collect output
+  int outbuf_cap = 0;
+  int* h_counters = nullptr;     // pinned mirror of counters
+  int* d_misc = nullptr;         // misc device ints (out counts, range)
+  int launches = 0;              // kernel launch counter (cumulative)
+};
+
+static int dev_alloc(flb_map* m, void** p, size_t bytes) {
+  CU(cudaMalloc(p, bytes));
+  m->device_bytes += bytes;
+  return 0;
+}
+
+static int map_reset_storage(flb_map* m) {
+  MapDev& d = m->d;
+  cudaStream_t st = m->stream;
+  CU(cudaMemsetAsync(d.keys, 0xFF, sizeof(uint64_t) * m->hash_cap, st));
+  CU(cudaMemsetAsync(d.vals, 0xFF, sizeof(uint32_t) * m->hash_cap, st));
+  CU(cudaMemsetAsync(d.bmask, 0, sizeof(uint64_t) * d.block_cap, st));
+  CU(cudaMemsetAsync(d.slots, 0xFF, sizeof(float4) * 64 * (size_t)d.block_cap, st));
+  CU(cudaMemsetAsync(d.bkey, 0xFF, sizeof(uint64_t) * d.block_cap, st));
+  CU(cudaMemsetAsync(d.ckeys, 0xFF, sizeof(uint64_t) * m->chash_cap, st));
+  CU(cudaMemsetAsync(d.cbits, 0, sizeof(uint64_t) * 8 * (size_t)m->chash_cap, st));
+  int init[CNT_COUNT];
+  memset(init, 0, sizeof(init));
+  init[CNT_CMIN_X] = init[CNT_CMIN_Y] = init[CNT_CMIN_Z] = INT_MAX;
+  init[CNT_CMAX_X] = init[CNT_CMAX_Y] = init[CNT_CMAX_Z] = INT_MIN;
+  memcpy(m->h_counters, init, sizeof(init));
+  CU(cudaMemcpyAsync(d.counters, m->h_counters, sizeof(init), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  m->has_root = false;
+  return 0;
+}
+
+static int fetch_counters(flb_map* m) {
+  CU(cudaMemcpyAsync(m->h_counters, m->d.counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  const int e = m->h_counters[CNT_ERROR];
+  if (e) {
+    return set_err("device map error flags 0x%x:%s%s%s%s%s", e, (e & ERR_BLOCKS_FULL) ? " block pool exhausted (raise max_blocks)" : "",
+                   (e & ERR_OVF_FULL) ? " overflow pool exhausted (raise max_points)" : "", (e & ERR_HASH_FULL) ? " block hash full" : "",
+                   (e & ERR_COARSE_FULL) ? " coarse hash full" : "", (e & ERR_RANGE) ? " point outside representable range / NaN" : "");
+  }
+  return 0;
+}
+
+extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
+  if (!cfg || !out) return set_err("flb_map_create: null argument");
+  if (!(cfg->voxel_size > 0.f)) return set_err("flb_map_create: voxel_size must be > 0");
+  int ndev = flb_device_count();
+  if (ndev <= 0) return set_err("flb_map_create: no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_err("flb_map_create: bad device %d", cfg->device);
+  CU(cudaSetDevice(cfg->device));
+  flb_map* m = new (std::nothrow) flb_map();
+  if (!m) return set_err("out of host memory");
+  m->cfg = *cfg;
+  if (m->cfg.max_points <= 0) m->cfg.max_points = 8 * 1024 * 1024;
+  if (m->cfg.max_blocks <= 0) m->cfg.max_blocks = std::max(4096, m->cfg.max_points / 4);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  m->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  MapDev& d = m->d;
+  d.ds = cfg->voxel_size;
+  d.block_cap = m->cfg.max_blocks;
+  d.ovf_cap = std::max(1024, m->cfg.max_points / 2);
+  m->hash_cap = next_pow2((uint64_t)d.block_cap * 2);
+  m->chash_cap = next_pow2(std::max<uint64_t>(1024, (uint64_t)d.block_cap / 8));
+  d.hash_mask = m->hash_cap - 1;
+  d.chash_mask = m->chash_cap - 1;
+  int rc = 0;
+  rc |= dev_alloc(m, (void**)&d.keys, sizeof(uint64_t) * m->hash_cap);
+  rc |= dev_alloc(m, (void**)&d.vals, sizeof(uint32_t) * m->hash_cap);
+  rc |= dev_alloc(m, (void**)&d.bmask, sizeof(uint64_t) * d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.slots, sizeof(float4) * 64 * (size_t)d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.ovf, sizeof(float4) * (size_t)d.ovf_cap);
+  rc |= dev_alloc(m, (void**)&d.bkey, sizeof(uint64_t) * d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.free_blk, sizeof(uint32_t) * d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.free_ovf, sizeof(uint32_t) * d.ovf_cap);
+  rc |= dev_alloc(m, (void**)&d.ckeys, sizeof(uint64_t) * m->chash_cap);
+  rc |= dev_alloc(m, (void**)&d.cbits, sizeof(uint64_t) * 8 * (size_t)m->chash_cap);
+  rc |= dev_alloc(m, (void**)&d.counters, sizeof(int) * CNT_COUNT);
+  rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 16);
+  if (rc) { flb_map_destroy(m); return 1; }
+  if (cudaMallocHost((void**)&m->h_counters, sizeof(int) * CNT_COUNT) != cudaSuccess) { flb_map_destroy(m); return set_err("cudaMallocHost failed"); }
+  // triangle index tables of the 13x13 augmented normal equations
+  unsigned char ti[91], tj[91];
+  int e = 0;
+  for (int i = 0; i < 13; ++i) for (int j = i; j < 13; ++j) { ti[e] = (unsigned char)i; tj[e] = (unsigned char)j; ++e; }
+  CU(cudaMemcpyToSymbol(c_tri_i, ti, sizeof(ti)));
+  CU(cudaMemcpyToSymbol(c_tri_j, tj, sizeof(tj)));
+  if (map_reset_storage(m)) { flb_map_destroy(m); return 1; }
+  *out = m;
+  return 0;
+}
+
+extern "C" void flb_map_destroy(flb_map* m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  MapDev& d = m->d;
+  void* ptrs[] = {d.keys, d.vals, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
+                  m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (m->h_counters) cudaFreeHost(m->h_counters);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+extern "C" int flb_map_set_downsample_param(flb_map* m, float v) {
+  if (!m) return set_err("null map");
+  if (!(v > 0.f)) return set_err("voxel size must be > 0");
+  if (v == m->d.ds) return 0;
+  CU(cudaSetDevice(m->cfg.device));
+  if (fetch_counters(m)) return 1;
+  if (m->h_counters[CNT_VALID] != 0) return set_err("set_downsample_param: map not empty (voxel hashing depends on the voxel size)");
+  m->d.ds = v;
+  m->cfg.voxel_size = v;
+  return 0;
+}
+extern "C" int flb_map_has_root(const flb_map* m) { return m && m->has_root ? 1 : 0; }
+
+// host strided xyz -> device float4 staging
+static int upload_points(flb_map* m, const float* xyz, int n, int stride) {
+  if (n <= 0) return 0;
+  if (!xyz) return set_err("null point buffer");
+  if (stride < 12) return set_err("stride_bytes must be >= 12");
+  if (n > m->stage_cap) {
+    if (m->stage) cudaFree(m->stage);
+    m->stage = nullptr;
+    m->stage_cap = 0;
+    int cap = std::max(n, 1 << 16);
+    CU(cudaMalloc((void**)&m->stage, sizeof(float4) * (size_t)cap));
+    m->stage_cap = cap;
+  }
+  if (stride == 16) {
+    CU(cudaMemcpyAsync(m->stage, xyz, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    return 0;
+  }
+  const size_t bytes = (size_t)(n - 1) * stride + 12;
+  if (bytes > m->raw_cap) {
+    if (m->raw) cudaFree(m->raw);
+    m->raw = nullptr;
+    m->raw_cap = 0;
+    size_t cap = std::max(bytes, (size_t)1 << 20);
+    CU(cudaMalloc((void**)&m->raw, cap));
+    m->raw_cap = cap;
+  }
+  CU(cudaMemcpyAsync(m->raw, xyz, bytes, cudaMemcpyHostToDevice, m->stream));
+  k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(m->raw, stride, m->stage, n);
+  m->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_scratch(flb_map* m, int n) {
+  uint32_t need = next_pow2((uint64_t)std::max(n, 512) * 2);
+  if (need > m->scratch_cap) {
+    if (m->skeys) cudaFree(m->skeys);
+    if (m->sbest) cudaFree(m->sbest);
+    m->skeys = nullptr; m->sbest = nullptr; m->scratch_cap = 0;
+    CU(cudaMalloc((void**)&m->skeys, sizeof(uint64_t) * need));
+    CU(cudaMalloc((void**)&m->sbest, sizeof(unsigned long long) * need));
+    m->scratch_cap = need;
+  }
+  return 0;
+}
+
+static int maybe_rehash(flb_map* m);
+
+// Insert device points. mode 0: verbatim (Build / Add_Points(false)); 1: downsample (Add_Points(true));
+// 2: classified (map_incremental: cls 1 -> downsample, cls 2 -> verbatim). Asynchronous on m->stream.
+static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode) {
+  if (n <= 0) return 0;
+  const int g = grid_for(n, 256, m->sm_count * 8);
+  cudaStream_t st = m->stream;
+  const unsigned char* c = (mode == 2) ? cls : nullptr;
+  k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n);
+  m->launches++;
+  if (mode == 1 || mode == 2) {
+    if (ensure_scratch(m, n)) return 1;
+    const uint32_t sc = next_pow2((uint64_t)std::max(n, 512) * 2);
+    CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
+    CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
+    k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1);
+    k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1);
+    m->launches += 2;
+  }
+  if (mode == 0 || mode == 2) {
+    k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n);
+    m->launches++;
+  }
+  CU(cudaGetLastError());
+  m->has_root = true;
+  return 0;
+}
+
+static int zero_scratch_counters(flb_map* m) {
+  CU(cudaMemsetAsync(m->d.counters + CNT_SCRATCH0, 0, sizeof(int) * 3, m->stream));
+  return 0;
+}
+
+extern "C" int flb_map_build(flb_map* m, const float* xyz, int n, int stride) {
+  if (!m) return set_err("null map");
+  if (n < 0) return set_err("negative point count");
+  CU(cudaSetDevice(m->cfg.device));
+  if (map_reset_storage(m)) return 1;
+  if (n == 0) return 0;  // Build with an empty cloud leaves Root_Node == nullptr (ikd_Tree.cpp:357)
+  if (upload_points(m, xyz, n, stride)) return 1;
+  if (insert_device(m, m->stage, nullptr, n, 0)) return 1;
+  return fetch_counters(m);
+}
+extern "C" int flb_map_reconstruct(flb_map* m, const float* xyz, int n, int stride) { return flb_map_build(m, xyz, n, stride); }
+
+extern "C" int flb_map_add_points(flb_map* m, const float* xyz, int n, int stride, int downsample_on, int* n_added) {
+  if (!m) return set_err("null map");
+  if (n_added) *n_added = 0;
+  if (n <= 0) return 0;
+  CU(cudaSetDevice(m->cfg.device));
+  if (upload_points(m, xyz, n, stride)) return 1;
+  if (zero_scratch_counters(m)) return 1;
+  if (insert_device(m, m->stage, nullptr, n, downsample_on ? 1 : 0)) return 1;
+  if (fetch_counters(m)) return 1;
+  // reference return value: tmp_counter counts downsample add ops only (ikd_Tree.cpp:447,457,488)
+  if (n_added) *n_added = downsample_on ? m->h_counters[CNT_SCRATCH0] : 0;
+  return 0;
+}
+
+static int upload_params(flb_map* m, const float* host, int nfloats) {
+  if (nfloats > m->dparams_cap) {
+    if (m->dparams) cudaFree(m->dparams);
+    m->dparams = nullptr; m->dparams_cap = 0;
+    int cap = std::max(nfloats, 256);
+    CU(cudaMalloc((void**)&m->dparams, sizeof(float) * cap));
+    m->dparams_cap = cap;
+  }
+  CU(cudaMemcpyAsync(m->dparams, host, sizeof(float) * nfloats, cudaMemcpyHostToDevice, m->stream));
+  return 0;
+}
+
+static int blocks_bumped(flb_map* m) {
+  // number of block indices ever handed out (dense iteration range); needs fresh counters
+  int b = m->h_counters[CNT_BLK_BUMP];
+  return b > m->d.block_cap ? m->d.block_cap : b;
+}
+
+static int delete_common(flb_map* m, const float* params, int np, int floats_per, int mode, int* n_deleted) {
+  if (n_deleted) *n_deleted = 0;
+  if (np <= 0) return 0;
+  CU(cudaSetDevice(m->cfg.device));
+  if (fetch_counters(m)) return 1;
+  const int nblk = blocks_bumped(m);
+  if (nblk == 0) return 0;
+  if (upload_params(m, params, np * floats_per)) return 1;
+  if (zero_scratch_counters(m)) return 1;
+  const int g = grid_for(nblk * 32, 256, m->sm_count * 8);
+  k_delete<<<g, 256, 0, m->stream>>>(m->d, m->dparams, np, mode, nblk);
+  m->launches++;
+  CU(cudaGetLastError());
+  if (fetch_counters(m)) return 1;
+  if (n_deleted) *n_deleted = m->h_counters[CNT_SCRATCH0];
+  return maybe_rehash(m);
+}
+
+extern "C" int flb_map_delete_boxes(flb_map* m, const float* boxes6, int nb, int* n_deleted) {
+  if (!m) return set_err("null map");
+  if (nb > 0 && !boxes6) return set_err("null boxes");
+  return delete_common(m, boxes6, nb, 6, 0, n_deleted);
+}
+extern "C" int flb_map_delete_points(flb_map* m, const float* xyz, int n, int stride, int* n_deleted) {
+  if (!m) return set_err("null map");
+  if (n > 0 && (!xyz || stride < 12)) return set_err("bad point buffer");
+  std::vector<float> p((size_t)std::max(n, 0) * 4);
+  for (int i = 0; i < n; ++i) {
+    const float* s = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(xyz) + (size_t)i * stride);
+    p[4 * i] = s[0]; p[4 * i + 1] = s[1]; p[4 * i + 2] = s[2]; p[4 * i + 3] = 0.f;
+  }
+  return delete_common(m, p.data(), n, 4, 1, n_deleted);
+}
+
+static int maybe_rehash(flb_map* m) {
+  // tombstones only lengthen probe chains; rebuild the key table (16 MB-ish, no point data moves) when they pile up
+  if (m->h_counters[CNT_KEYS_TOMB] <= (int)(m->hash_cap / 8)) return 0;
+  const int nblk = blocks_bumped(m);
+  cudaStream_t st = m->stream;
+  CU(cudaMemsetAsync(m->d.keys, 0xFF, sizeof(uint64_t) * m->hash_cap, st));
+  CU(cudaMemsetAsync(m->d.vals, 0xFF, sizeof(uint32_t) * m->hash_cap, st));
+  CU(cudaMemsetAsync(m->d.ckeys, 0xFF, sizeof(uint64_t) * m->chash_cap, st));
+  CU(cudaMemsetAsync(m->d.cbits, 0, sizeof(uint64_t) * 8 * (size_t)m->chash_cap, st));
+  int init[8] = {0, 0, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  // KEYS_TOMB = 0, COARSE_USED = 0, bbox reset
+  CU(cudaMemcpyAsync(m->d.counters + CNT_KEYS_TOMB, &init[0], sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->d.counters + CNT_COARSE_USED, &init[1], sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->d.counters + CNT_CMIN_X, &init[2], sizeof(int) * 6, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));  // init[] is a stack buffer
+  k_rehash_insert<<<grid_for(nblk, 256, m->sm_count * 8), 256, 0, st>>>(m->d, nblk);
+  m->launches++;
+  CU(cudaGetLastError());
+  m->rehash_count++;
+  return fetch_counters(m);
+}
+
+template <int K>
+static void launch_knn(flb_map* m, const KnnArgs& a) {
+  const int g = grid_for(a.n * 32, 128, m->sm_count * 16);
+  k_knn<K><<<g, 128, 0, m->stream>>>(a);
+  m->launches++;
+}
+
+static int ensure_outbuf(flb_map* m, int n) {
+  if (n > m->outbuf_cap) {
+    if (m->outbuf) cudaFree(m->outbuf);
+    m->outbuf = nullptr; m->outbuf_cap = 0;
+    int cap = std::max(n, 1 << 16);
+    CU(cudaMalloc((void**)&m->outbuf, sizeof(float4) * (size_t)cap));
+    m->outbuf_cap = cap;
+  }
+  return 0;
+}
+
+extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, int stride, int k, float max_dist,
+                                      float* out_xyz, float* out_d2, int* out_cnt) {
+  if (!m) return set_err("null map");
+  if (k < 1 || k > 20) return set_err("Nearest_Search: k must be in [1,20]");
+  if (nq <= 0) return 0;
+  CU(cudaSetDevice(m->cfg.device));
+  if (upload_points(m, q_xyz, nq, stride)) return 1;
+  const int K = k <= 5 ? 5 : 20;
+  if (ensure_outbuf(m, nq * K)) return 1;
+  unsigned char* dcnt = nullptr;
+  CU(cudaMalloc((void**)&dcnt, nq));
+  KnnArgs a;
+  a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt;
+  a.max_d2 = (max_dist > 0.f && max_dist < 1e18f) ? max_dist * max_dist : INFINITY;
+  a.phase_stats = nullptr;
+  if (K == 5) launch_knn<5>(m, a); else launch_knn<20>(m, a);
+  cudaError_t le = cudaGetLastError();
+  std::vector<float4> h((size_t)nq * K);
+  std::vector<unsigned char> hc(nq);
+  if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), m->outbuf, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost, m->stream);
+  if (le == cudaSuccess) le = cudaMemcpyAsync(hc.data(), dcnt, nq, cudaMemcpyDeviceToHost, m->stream);
+  if (le == cudaSuccess) le = cudaStreamSynchronize(m->stream);
+  cudaFree(dcnt);
+  if (le != cudaSuccess) return set_err("nearest_search failed: %s", cudaGetErrorString(le));
+  for (int i = 0; i < nq; ++i) {
+    const int c = std::min<int>(hc[i], k);
+    if (out_cnt) out_cnt[i] = c;
+    for (int j = 0; j < k; ++j) {
+      const float4 v = h[(size_t)j * nq + i];
+      const bool ok = j < c;
+      if (out_xyz) {
+        out_xyz[((size_t)i * k + j) * 3 + 0] = ok ? v.x : NAN;
+        out_xyz[((size_t)i * k + j) * 3 + 1] = ok ? v.y : NAN;
+        out_xyz[((size_t)i * k + j) * 3 + 2] = ok ? v.z : NAN;
+      }
+      if (out_d2) out_d2[(size_t)i * k + j] = ok ? v.w : INFINITY;
+    }
+  }
+  return 0;
+}
+
+static int collect_common(flb_map* m, int mode, const float* params, int nparams, float* out_xyz, int cap, int* n_found) {
+  if (n_found) *n_found = 0;
+  CU(cudaSetDevice(m->cfg.device));
+  if (fetch_counters(m)) return 1;
+  const int nblk = blocks_bumped(m);
+  if (nblk == 0) return 0;
+  if (cap < 0) cap = 0;
+  if (!out_xyz) cap = 0;
+  if (cap > 0 && ensure_outbuf(m, cap)) return 1;
+  if (nparams && upload_params(m, params, nparams)) return 1;
+  CU(cudaMemsetAsync(m->d_misc, 0, sizeof(int), m->stream));
+  k_collect<<<grid_for(nblk * 32, 256, m->sm_count * 8), 256, 0, m->stream>>>(m->d, nblk, mode, m->dparams, cap ? m->outbuf : nullptr, cap, m->d_misc);
+  m->launches++;
+  CU(cudaGetLastError());
+  int total = 0;
+  CU(cudaMemcpyAsync(&total, m->d_misc, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  if (n_found) *n_found = total;
+  const int w = std::min(total, cap);
+  if (w > 0) {
+    std::vector<float4> h(w);
+    CU(cudaMemcpy(h.data(), m->outbuf, sizeof(float4) * w, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < w; ++i) { out_xyz[3 * i] = h[i].x; out_xyz[3 * i + 1] = h[i].y; out_xyz[3 * i + 2] = h[i].z; }
+  }
+  return 0;
+}
+extern "C" int flb_map_flatten(flb_map* m, float* out_xyz, int cap, int* n) {
+  if (!m) return set_err("null map");
+  return collect_common(m, 0, nullptr, 0, out_xyz, cap, n);
+}
+extern "C" int flb_map_box_search(flb_map* m, const float* box6, float* out_xyz, int cap, int* n_found) {
+  if (!m || !box6) return set_err("null argument");
+  return collect_common(m, 1, box6, 6, out_xyz, cap, n_found);
+}
+extern "C" int flb_map_radius_search(flb_map* m, const float* c, float radius, float* out_xyz, int cap, int* n_found) {
+  if (!m || !c) return set_err("null argument");
+  const float p[4] = {c[0], c[1], c[2], radius};
+  return collect_common(m, 2, p, 4, out_xyz, cap, n_found);
+}
+extern "C" int flb_map_validnum(flb_map* m) {
+  if (!m) return -1;
+  if (cudaSetDevice(m->cfg.device) != cudaSuccess) return -1;
+  if (fetch_counters(m)) return -1;
+  return m->h_counters[CNT_VALID];
+}
+extern "C" int flb_map_size(flb_map* m) { return flb_map_validnum(m); }
+
+extern "C" int flb_map_range(flb_map* m, float* box6) {
+  if (!m || !box6) return set_err("null argument");
+  CU(cudaSetDevice(m->cfg.device));
+  if (fetch_counters(m)) return 1;
+  const int nblk = blocks_bumped(m);
+  int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  CU(cudaMemcpyAsync(m->d_misc + 4, init, sizeof(init), cudaMemcpyHostToDevice, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  if (nblk) {
+    k_range<<<grid_for(nblk * 32, 256, m->sm_count * 8), 256, 0, m->stream>>>(m->d, nblk, m->d_misc + 4);
+    m->launches++;
+  }
+  int o[6];
+  CU(cudaMemcpyAsync(o, m->d_misc + 4, sizeof(o), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  for (int i = 0; i < 6; ++i) {
+    int v = o[i];
+    if (v == INT_MAX || v == INT_MIN) { box6[i] = (i < 3) ? INFINITY : -INFINITY; continue; }
+    int bits = v >= 0 ? v : v ^ 0x7FFFFFFF;
+    memcpy(&box6[i], &bits, 4);
+  }
+  return 0;
+}
+
+extern "C" int flb_map_get_stats(flb_map* m, flb_map_stats* out) {
+  if (!m || !out) return set_err("null argument");
+  CU(cudaSetDevice(m->cfg.device));
+  if (fetch_counters(m)) return 1;
+  const int* c = m->h_counters;
+  out->valid_points = c[CNT_VALID];
+  out->blocks_in_use = std::min(c[CNT_BLK_BUMP], m->d.block_cap) - c[CNT_BLK_FREE];
+  out->block_capacity = m->d.block_cap;
+  out->overflow_in_use = std::min(c[CNT_OVF_BUMP], m->d.ovf_cap) - c[CNT_OVF_FREE];
+  out->overflow_capacity = m->d.ovf_cap;
+  out->hash_capacity = (int)m->hash_cap;
+  out->hash_tombstones = c[CNT_KEYS_TOMB];
+  out->coarse_cells = c[CNT_COARSE_USED];
+  out->rehash_count = m->rehash_count;
+  out->device_bytes = m->device_bytes;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ session
+struct flb_session {
+  flb_map* map = nullptr;
+  flb_session_config cfg{};
+  int cap = 0, n = 0;
+  float4 *body = nullptr, *world = nullptr, *nbr = nullptr, *normvec = nullptr;
+  unsigned char *cnt = nullptr, *sel = nullptr, *cls = nullptr;
+  double *partial = nullptr, *dout = nullptr;
+  int* offs = nullptr;
+  int* selint = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  double* drows = nullptr;  // M x 13 export buffer
+  int drows_cap = 0;
+  double* h_out = nullptr;  // pinned NACC
+  int* h_cnt2 = nullptr;    // pinned 4 ints
+  int* d_cnt2 = nullptr;
+  int res_grid = 0;
+  PoseDev last_pose{};
+  bool have_pass = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  unsigned char* raw = nullptr;
+  size_t raw_cap = 0;
+};
+
+extern "C" void flb_session_default_config(flb_session_config* c) {
+  if (!c) return;
+  c->max_scan_points = 131072;
+  c->extrinsic_est_en = 0;
+  c->max_iterations = 4;  // NUM_MAX_ITERATIONS default, laserMapping.cpp:2064
+  c->laser_point_cov = 0.001;
+  c->filter_size_map_min = 0.2;
+  for (int i = 0; i < FLB_STATE_DOF; ++i) c->limit[i] = 0.001;
+}
+
+extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb_session** out) {
+  if (!m || !cfg || !out) return set_err("flb_session_create: null argument");
+  if (cfg->max_scan_points <= 0) return set_err("max_scan_points must be > 0");
+  CU(cudaSetDevice(m->cfg.device));
+  flb_session* s = new (std::nothrow) flb_session();
+  if (!s) return set_err("out of host memory");
+  s->map = m;
+  s->cfg = *cfg;
+  s->cap = cfg->max_scan_points;
+  const size_t N = (size_t)s->cap;
+  s->res_grid = m->sm_count * 2;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); };
+  A((void**)&s->body, sizeof(float4) * N);
+  A((void**)&s->world, sizeof(float4) * N);
+  A((void**)&s->nbr, sizeof(float4) * N * 5);
+  A((void**)&s->normvec, sizeof(float4) * N);
+  A((void**)&s->cnt, N);
+  A((void**)&s->sel, N);
+  A((void**)&s->cls, N);
+  A((void**)&s->partial, sizeof(double) * NACC * (size_t)s->res_grid);
+  A((void**)&s->dout, sizeof(double) * NACC);
+  A((void**)&s->offs, sizeof(int) * N);
+  A((void**)&s->selint, sizeof(int) * N);
+  A((void**)&s->d_cnt2, sizeof(int) * 8);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_out, sizeof(double) * NACC);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_cnt2, sizeof(int) * 8);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
+  if (e == cudaSuccess) {
+    size_t tb = 0;
+    e = cub::DeviceScan::ExclusiveSum(nullptr, tb, s->selint, s->offs, s->cap, m->stream);
+    s->cub_tmp_bytes = tb;
+    A(&s->cub_tmp, tb ? tb : 16);
+  }
+  if (e != cudaSuccess) { flb_session_destroy(s); return set_err("flb_session_create: %s", cudaGetErrorString(e)); }
+  *out = s;
+  return 0;
+}
+
+extern "C" void flb_session_destroy(flb_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->map->cfg.device);
+  cudaStreamSynchronize(s->map->stream);
+  void* ptrs[] = {s->body, s->world, s->nbr, s->normvec, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
+                  s->cub_tmp, s->drows, s->d_cnt2, s->raw};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (s->h_out) cudaFreeHost(s->h_out);
+  if (s->h_cnt2) cudaFreeHost(s->h_cnt2);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev2) cudaEventDestroy(s->ev2);
+  if (s->ev3) cudaEventDestroy(s->ev3);
+  delete s;
+}
+
+extern "C" void* flb_session_stream(flb_session* s) { return s ? (void*)s->map->stream : nullptr; }
+extern "C" int flb_session_sync(flb_session* s) {
+  if (!s) return set_err("null session");
+  CU(cudaStreamSynchronize(s->map->stream));
+  return 0;
+}
+
+static int scan_reset(flb_session* s, int n) {
+  s->n = n;
+  s->have_pass = false;
+  // memset(point_selected_surf, true) (laserMapping.cpp:2131); Nearest_Points empty
+  CU(cudaMemsetAsync(s->sel, 1, (size_t)std::max(n, 1), s->map->stream));
+  CU(cudaMemsetAsync(s->cnt, 0, (size_t)std::max(n, 1), s->map->stream));
+  return 0;
+}
+
+extern "C" int flb_scan_upload(flb_session* s, const float* xyz, int n, int stride) {
+  if (!s) return set_err("null session");
+  if (n < 0 || n > s->cap) return set_err("scan of %d points exceeds max_scan_points=%d", n, s->cap);
+  if (n > 0 && (!xyz || stride < 12)) return set_err("bad scan buffer");
+  CU(cudaSetDevice(s->map->cfg.device));
+  flb_map* m = s->map;
+  if (n > 0) {
+    if (stride == 16) {
+      CU(cudaMemcpyAsync(s->body, xyz, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    } else {
+      const size_t bytes = (size_t)(n - 1) * stride + 12;
+      if (bytes > s->raw_cap) {
+        if (s->raw) cudaFree(s->raw);
+        s->raw = nullptr; s->raw_cap = 0;
+        CU(cudaMalloc((void**)&s->raw, std::max(bytes, (size_t)1 << 20)));
+        s->raw_cap = std::max(bytes, (size_t)1 << 20);
+      }
+      CU(cudaMemcpyAsync(s->raw, xyz, bytes, cudaMemcpyHostToDevice, m->stream));
+      k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(s->raw, stride, s->body, n);
+      m->launches++;
+      CU(cudaGetLastError());
+    }
+  }
+  return scan_reset(s, n);
+}
+
+extern "C" int flb_scan_set_device(flb_session* s, const void* body4_dev, int n) {
+  if (!s) return set_err("null session");
+  if (n < 0 || n > s->cap) return set_err("scan of %d points exceeds max_scan_points=%d", n, s->cap);
+  CU(cudaSetDevice(s->map->cfg.device));
+  if (n > 0) CU(cudaMemcpyAsync(s->body, body4_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, s->map->stream));
+  return scan_reset(s, n);
+}
+
+static PoseDev pose_from(const double* st) {
+  PoseDev p;
+  for (int i = 0; i < 4; ++i) { p.rot[i] = st[3 + i]; p.offR[i] = st[7 + i]; }
+  for (int i = 0; i < 3; ++i) { p.pos[i] = st[i]; p.offT[i] = st[11 + i]; }
+  return p;
+}
+
+static MeasArgs meas_args(flb_session* s, const PoseDev& pose, int search) {
+  MeasArgs a;
+  a.pose = pose; a.body = s->body; a.world = s->world; a.nbr = s->nbr; a.cnt = s->cnt; a.sel = s->sel;
+  a.normvec = s->normvec; a.partial = s->partial; a.n = s->n; a.search = search;
+  return a;
+}
+
+// enqueue one pass (no sync). The reduced result lands in s->h_out after the stream drains.
+static int enqueue_pass(flb_session* s, const double* state26, int search) {
+  flb_map* m = s->map;
+  cudaStream_t st = m->stream;
+  const int n = s->n;
+  const PoseDev pose = pose_from(state26);
+  s->last_pose = pose;
+  k_transform<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->world, n);
+  m->launches++;
+  if (search) {
+    KnnArgs a;
+    a.m = m->d; a.q = s->world; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY; a.phase_stats = nullptr;
+    launch_knn<5>(m, a);
+  }
+  const MeasArgs ma = meas_args(s, pose, search);
+  if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+  else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+  k_reduce_final<<<1, 384, 0, st>>>(s->partial, s->res_grid, s->dout);
+  m->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(s->h_out, s->dout, sizeof(double) * NACC, cudaMemcpyDeviceToHost, st));
+  s->have_pass = true;
+  return 0;
+}
+
+static void unpack_result(const double* o, flb_pass_result* r) {
+  auto slot = [](int i, int j) { return i * 13 - i * (i - 1) / 2 + (j - i); };
+  for (int i = 0; i < 12; ++i) {
+    for (int j = i; j < 12; ++j) { r->HTH[i * 12 + j] = o[slot(i, j)]; r->HTH[j * 12 + i] = o[slot(i, j)]; }
+    r->HTh[i] = o[slot(i, 12)];
+  }
+  r->total_residual = o[91];
+  r->effct_feat_num = (int)(o[92] + 0.5);
+  r->valid = r->effct_feat_num >= 1;
+}
+
+extern "C" int flb_pass(flb_session* s, const double* state26, int search, flb_pass_result* out) {
+  if (!s || !state26 || !out) return set_err("flb_pass: null argument");
+  CU(cudaSetDevice(s->map->cfg.device));
+  memset(out, 0, sizeof(*out));
+  if (s->n <= 0) { out->valid = 0; return 0; }
+  if (enqueue_pass(s, state26, search)) return 1;
+  CU(cudaStreamSynchronize(s->map->stream));
+  unpack_result(s->h_out, out);
+  return 0;
+}
+
+// device export of rows in index order; returns M
+static int export_rows(flb_session* s, int M_expected) {
+  flb_map* m = s->map;
+  cudaStream_t st = m->stream;
+  const int n = s->n;
+  if (M_expected > s->drows_cap) {
+    if (s->drows) cudaFree(s->drows);
+    s->drows = nullptr; s->drows_cap = 0;
+    int cap = std::max(M_expected, 1 << 14);
+    CU(cudaMalloc((void**)&s->drows, sizeof(double) * 13 * (size_t)cap));
+    s->drows_cap = cap;
+  }
+  const int g = grid_for(n, 256, m->sm_count * 8);
+  k_sel_to_int<<<g, 256, 0, st>>>(s->sel, s->selint, n);
+  size_t tb = s->cub_tmp_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(s->cub_tmp, tb, s->selint, s->offs, n, st));
+  const MeasArgs ma = meas_args(s, s->last_pose, 0);
+  const int ld = s->drows_cap;
+  if (s->cfg.extrinsic_est_en) k_rows<true><<<g, 256, 0, st>>>(ma, s->offs, s->drows, ld, s->drows + (size_t)12 * ld, s->drows_cap);
+  else k_rows<false><<<g, 256, 0, st>>>(ma, s->offs, s->drows, ld, s->drows + (size_t)12 * ld, s->drows_cap);
+  m->launches += 3;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int flb_pass_rows(flb_session* s, double* hx, int ld, double* h, int capacity_rows, int* M) {
+  if (!s || !M) return set_err("flb_pass_rows: null argument");
+  if (!s->have_pass) return set_err("flb_pass_rows: no preceding flb_pass for this scan");
+  CU(cudaSetDevice(s->map->cfg.device));
+  const int Mexp = (int)(s->h_out[92] + 0.5);
+  *M = Mexp;
+  if (Mexp == 0) return 0;
+  if (capacity_rows < Mexp || ld < Mexp) return set_err("flb_pass_rows: capacity %d / ld %d < M = %d", capacity_rows, ld, Mexp);
+  if (export_rows(s, Mexp)) return 1;
+  cudaStream_t st = s->map->stream;
+  const int dl = s->drows_cap;
+  if (hx) CU(cudaMemcpy2DAsync(hx, sizeof(double) * ld, s->drows, sizeof(double) * dl, sizeof(double) * Mexp, 12, cudaMemcpyDeviceToHost, st));
+  if (h) CU(cudaMemcpyAsync(h, s->drows + (size_t)12 * dl, sizeof(double) * Mexp, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int run_update(flb_session* s, double* state26, double* P, flb_update_stats* stats) {
+  flb_map* m = s->map;
+  host::IteratedUpdate u(state26, P, s->cfg.laser_point_cov, s->cfg.max_iterations, s->cfg.limit);
+  int passes = 0, searches = 0, lastM = 0;
+  double lastres = 0;
+  CU(cudaEventRecord(s->ev0, m->stream));
+  while (u.more()) {
+    double cur[26];
+    u.current_state(cur);
+    const int search = u.need_search() ? 1 : 0;
+    flb_pass_result r;
+    if (s->n <= 0) { u.skip(); ++passes; continue; }
+    if (enqueue_pass(s, cur, search)) return 1;
+    CU(cudaStreamSynchronize(m->stream));
+    unpack_result(s->h_out, &r);
+    ++passes;
+    searches += search;
+    if (!r.valid) { u.skip(); continue; }
+    lastM = r.effct_feat_num;
+    lastres = r.total_residual;
+    if (r.effct_feat_num >= host::DOF) {
+      u.step(r.HTH, r.HTh);
+    } else {
+      // rare under-determined branch (esekfom.hpp:1720-1750) needs the explicit rows
+      const int M = r.effct_feat_num;
+      if (export_rows(s, M)) return 1;
+      std::vector<double> cm((size_t)13 * M), rows((size_t)12 * M), hv(M);
+      const int dl = s->drows_cap;
+      CU(cudaMemcpy2DAsync(cm.data(), sizeof(double) * M, s->drows, sizeof(double) * dl, sizeof(double) * M, 13, cudaMemcpyDeviceToHost, m->stream));
+      CU(cudaStreamSynchronize(m->stream));
+      for (int r_ = 0; r_ < M; ++r_) { for (int c = 0; c < 12; ++c) rows[(size_t)r_ * 12 + c] = cm[(size_t)c * M + r_]; hv[r_] = cm[(size_t)12 * M + r_]; }
+      u.step_rows(rows.data(), hv.data(), M);
+    }
+  }
+  CU(cudaEventRecord(s->ev1, m->stream));
+  u.result(state26, P);
+  if (stats) {
+    stats->passes = passes; stats->search_passes = searches; stats->effct_feat_num = lastM;
+    stats->converged_count = u.converged_count(); stats->total_residual = lastres;
+    CU(cudaEventSynchronize(s->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    stats->gpu_ms = ms;
+  }
+  return 0;
+}
+
+extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_update_stats* stats) {
+  if (!s || !state26 || !P) return set_err("flb_esikf_update: null argument");
+  CU(cudaSetDevice(s->map->cfg.device));
+  return run_update(s, state26, P, stats);
+}
+
+static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited) {
+  flb_map* m = s->map;
+  cudaStream_t st = m->stream;
+  const int n = s->n;
+  if (n <= 0) return 0;
+  const PoseDev pose = pose_from(state26);
+  CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
+  k_classify<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->nbr, s->cnt, n, flg_EKF_inited,
+                                                                s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
+  m->launches++;
+  CU(cudaGetLastError());
+  if (insert_device(m, s->world, s->cls, n, 2)) return 1;
+  CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int flb_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, int* n_to_add, int* n_no_ds) {
+  if (!s || !state26) return set_err("flb_map_incremental: null argument");
+  CU(cudaSetDevice(s->map->cfg.device));
+  if (n_to_add) *n_to_add = 0;
+  if (n_no_ds) *n_no_ds = 0;
+  if (s->n <= 0) return 0;
+  if (enqueue_map_incremental(s, state26, flg_EKF_inited)) return 1;
+  if (fetch_counters(s->map)) return 1;
+  if (n_to_add) *n_to_add = s->h_cnt2[0];
+  if (n_no_ds) *n_no_ds = s->h_cnt2[1];
+  return 0;
+}
+
+extern "C" int flb_neighbors_download(flb_session* s, float* nbr_xyz, float* nbr_d2, int* nbr_cnt, unsigned char* selected,
+                                      float* normvec, float* world_xyz) {
+  if (!s) return set_err("null session");
+  CU(cudaSetDevice(s->map->cfg.device));
+  const int n = s->n;
+  if (n <= 0) return 0;
+  cudaStream_t st = s->map->stream;
+  std::vector<float4> h4;
+  std::vector<unsigned char> hc(n);
+  if (nbr_xyz || nbr_d2) {
+    h4.resize((size_t)5 * n);
+    CU(cudaMemcpyAsync(h4.data(), s->nbr, sizeof(float4) * h4.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hc.data(), s->cnt, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < 5; ++j) {
+        const bool ok = j < hc[i];
+        const float4 v = h4[(size_t)j * n + i];
+        if (nbr_xyz) { nbr_xyz[((size_t)i * 5 + j) * 3] = ok ? v.x : NAN; nbr_xyz[((size_t)i * 5 + j) * 3 + 1] = ok ? v.y : NAN; nbr_xyz[((size_t)i * 5 + j) * 3 + 2] = ok ? v.z : NAN; }
+        if (nbr_d2) nbr_d2[(size_t)i * 5 + j] = ok ? v.w : INFINITY;
+      }
+  }
+  if (nbr_cnt) {
+    CU(cudaMemcpyAsync(hc.data(), s->cnt, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) nbr_cnt[i] = hc[i];
+  }
+  if (selected) { CU(cudaMemcpyAsync(selected, s->sel, n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+  if (normvec) { CU(cudaMemcpyAsync(normvec, s->normvec, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+  if (world_xyz) {
+    h4.resize(n);
+    CU(cudaMemcpyAsync(h4.data(), s->world, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) { world_xyz[3 * i] = h4[i].x; world_xyz[3 * i + 1] = h4[i].y; world_xyz[3 * i + 2] = h4[i].z; }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fov segment
+// Host logic of lasermap_fov_segment (laserMapping.cpp:1136-1200); the delete itself runs on the device.
+static int fov_boxes(flb_fov_state* f, const double* pos, float* boxes, int* nb) {
+  const float MOV_THRESHOLD = 1.5f;  // laserMapping.cpp:53
+  *nb = 0;
+  if (!f->initialized) {
+    for (int i = 0; i < 3; ++i) {
+      f->local_map_min[i] = (float)(pos[i] - f->cube_len / 2.0);
+      f->local_map_max[i] = (float)(pos[i] + f->cube_len / 2.0);
+    }
+    f->initialized = 1;
+    return 0;
+  }
+  float edge[3][2];
+  bool need_move = false;
+  const float lim = MOV_THRESHOLD * f->det_range;
+  for (int i = 0; i < 3; ++i) {
+    edge[i][0] = (float)std::fabs(pos[i] - (double)f->local_map_min[i]);
+    edge[i][1] = (float)std::fabs(pos[i] - (double)f->local_map_max[i]);
+    if (edge[i][0] <= lim || edge[i][1] <= lim) need_move = true;
+  }
+  if (!need_move) return 0;
+  float nmin[3], nmax[3];
+  for (int i = 0; i < 3; ++i) { nmin[i] = f->local_map_min[i]; nmax[i] = f->local_map_max[i]; }
+  const float mov = (float)std::max((f->cube_len - 2.0 * MOV_THRESHOLD * f->det_range) * 0.5 * 0.9,
+                                    double(f->det_range * (MOV_THRESHOLD - 1)));
+  for (int i = 0; i < 3; ++i) {
+    float b[6] = {f->local_map_min[0], f->local_map_min[1], f->local_map_min[2], f->local_map_max[0], f->local_map_max[1], f->local_map_max[2]};
+    if (edge[i][0] <= lim) {
+      nmax[i] -= mov; nmin[i] -= mov;
+      b[i] = f->local_map_max[i] - mov;
+      memcpy(boxes + 6 * (*nb), b, sizeof(b));
+      ++*nb;
+    } else if (edge[i][1] <= lim) {
+      nmax[i] += mov; nmin[i] += mov;
+      b[3 + i] = f->local_map_min[i] + mov;
+      memcpy(boxes + 6 * (*nb), b, sizeof(b));
+      ++*nb;
+    }
+  }
+  for (int i = 0; i < 3; ++i) { f->local_map_min[i] = nmin[i]; f->local_map_max[i] = nmax[i]; }
+  return 0;
+}
+
+extern "C" int flb_fov_segment(flb_map* m, flb_fov_state* fov, const double* pos_lid, float* boxes_out18, int* n_boxes, int* n_deleted) {
+  if (!m || !fov || !pos_lid) return set_err("flb_fov_segment: null argument");
+  float boxes[18];
+  int nb = 0;
+  fov_boxes(fov, pos_lid, boxes, &nb);
+  if (boxes_out18) memcpy(boxes_out18, boxes, sizeof(float) * 6 * nb);
+  if (n_boxes) *n_boxes = nb;
+  if (n_deleted) *n_deleted = 0;
+  if (nb > 0) return flb_map_delete_boxes(m, boxes, nb, n_deleted);  // :1197-1198
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ whole scan step
+extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body, int n, int stride, double* state26, double* P,
+                             int flg_EKF_inited, flb_scan_result* out) {
+  if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
+  flb_map* m = s->map;
+  CU(cudaSetDevice(m->cfg.device));
+  const int l0 = m->launches;
+  flb_scan_result r;
+  memset(&r, 0, sizeof(r));
+  CU(cudaEventRecord(s->ev2, m->stream));
+  if (body) { if (flb_scan_upload(s, body, n, stride)) return 1; }
+  if (fov) {  // laserMapping.cpp:2320 (uses pos_lid of the previous posterior)
+    int nb = 0;
+    if (flb_fov_segment(m, fov, fov->pos_lid, nullptr, &nb, &r.n_deleted)) return 1;
+  }
+  if (run_update(s, state26, P, &r.update)) return 1;  // :2380
+  if (fov) {  // :2383 pos_lid = pos + rot * offset_T_L_I
+    host::State x = host::State::from26(state26);
+    host::V3 pl = x.pos + host::rotate(x.rot, x.offT);
+    for (int i = 0; i < 3; ++i) fov->pos_lid[i] = pl.a[i];
+  }
+  if (s->n > 0) {  // :2401
+    if (enqueue_map_incremental(s, state26, flg_EKF_inited)) return 1;
+  }
+  CU(cudaEventRecord(s->ev3, m->stream));
+  if (fetch_counters(m)) return 1;
+  r.n_to_add = s->n > 0 ? s->h_cnt2[0] : 0;
+  r.n_no_downsample = s->n > 0 ? s->h_cnt2[1] : 0;
+  r.map_valid = m->h_counters[CNT_VALID];
+  CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
+  r.kernel_launches = m->launches - l0;
+  if (out) *out = r;
+  return maybe_rehash(m);
+}

@@ -1,0 +1,310 @@
+// knn_kernels.cuh — K1: exact k-nearest-neighbour search on the hashed voxel map, one warp per query.
+// Replaces KD_TREE::Nearest_Search / Search (include/ikd-Tree/ikd_Tree.cpp:366-397, :868-1013) as called from
+// h_share_model (src/laserMapping.cpp:1909).  Semantics kept: exact over all valid points, unbounded range
+// (max_dist = INFINITY by default, ikd_Tree.h:236), float squared distances ((dx*dx+dy*dy)+dz*dz, no FMA —
+// calc_dist ikd_Tree.cpp:1373-1378), ascending output, fewer than k results when the map is small.
+// Equal-distance ties are broken by (x,y,z) — the reference's order depends on tree traversal (ikd_Tree.h:102-105).
+//
+// Search plan per query (all exact, each phase only runs if the previous one could not prove completeness):
+//   A  5x5x5 voxel stencil around the query voxel (always inside 2x2x2 blocks; 8 hash probes by lanes 0-7)
+//   B  the 3x3x3 coarse cells (8x8x8 blocks each) around the query, block bitmaps prune by box distance
+//   C  every other coarse cell in the coarse hash (far queries at the map frontier; rare)
+// Completeness test: have k candidates and d_k < (distance from the query to the boundary of the searched region)^2.
+// Roofline: HBM/L2-latency bound gather; algorithmic bytes 16 (query) + 80 (5 neighbours) + 80 (cache write).
+#pragma once
+#include "voxel_map.cuh"
+#include <math_constants.h>
+
+namespace flb {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int K>
+struct TopK {
+  float d[K], x[K], y[K], z[K];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int j = 0; j < K; ++j) { d[j] = CUDART_INF_F; x[j] = 0.f; y[j] = 0.f; z[j] = 0.f; }
+  }
+  static __device__ __forceinline__ bool less(float da, float xa, float ya, float za, float db, float xb, float yb, float zb) {
+    if (da != db) return da < db;
+    if (xa != xb) return xa < xb;
+    if (ya != yb) return ya < yb;
+    return za < zb;
+  }
+  __device__ __forceinline__ void insert(float dd, float px, float py, float pz) {
+    if (!less(dd, px, py, pz, d[K - 1], x[K - 1], y[K - 1], z[K - 1])) return;
+    d[K - 1] = dd; x[K - 1] = px; y[K - 1] = py; z[K - 1] = pz;
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+      if (less(d[j], x[j], y[j], z[j], d[j - 1], x[j - 1], y[j - 1], z[j - 1])) {
+        float t;
+        t = d[j]; d[j] = d[j - 1]; d[j - 1] = t;
+        t = x[j]; x[j] = x[j - 1]; x[j - 1] = t;
+        t = y[j]; y[j] = y[j - 1]; y[j - 1] = t;
+        t = z[j]; z[j] = z[j - 1]; z[j - 1] = t;
+      }
+    }
+  }
+  __device__ __forceinline__ void pop_front() {
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) { d[j] = d[j + 1]; x[j] = x[j + 1]; y[j] = y[j + 1]; z[j] = z[j + 1]; }
+    d[K - 1] = CUDART_INF_F;
+  }
+};
+
+__device__ __forceinline__ float sqdist(float qx, float qy, float qz, float px, float py, float pz) {
+  const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Merge the 32 lane-local sorted lists into the global top-K.  On return: lane r (< gcount) holds result r in
+// (rd,rx,ry,rz); every lane's list is cleared except lane r which re-inserts result r; returns gcount and the
+// current k-th distance (INF if fewer than K found) in thr.
+template <int K>
+__device__ __forceinline__ int warp_merge(TopK<K>& t, int lane, float& rd, float& rx, float& ry, float& rz, float& thr) {
+  int gcount = 0;
+  float last = CUDART_INF_F;
+  rd = CUDART_INF_F; rx = ry = rz = CUDART_NAN_F;
+#pragma unroll 1
+  for (int r = 0; r < K; ++r) {
+    const unsigned v = __float_as_uint(t.d[0]);
+    const unsigned mn = __reduce_min_sync(FULL, v);
+    if (mn == 0x7f800000u) break;
+    unsigned who = __ballot_sync(FULL, v == mn);
+    int src = __ffs(who) - 1;
+    if (who & (who - 1)) {  // several lanes tie on distance: lexicographic (x,y,z)
+      float bx = __shfl_sync(FULL, t.x[0], src), by = __shfl_sync(FULL, t.y[0], src), bz = __shfl_sync(FULL, t.z[0], src);
+      unsigned rest = who & ~(1u << src);
+      while (rest) {
+        const int c = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const float cx = __shfl_sync(FULL, t.x[0], c), cy = __shfl_sync(FULL, t.y[0], c), cz = __shfl_sync(FULL, t.z[0], c);
+        if (cx < bx || (cx == bx && (cy < by || (cy == by && cz < bz)))) { bx = cx; by = cy; bz = cz; src = c; }
+      }
+    }
+    const float gd = __shfl_sync(FULL, t.d[0], src), gx = __shfl_sync(FULL, t.x[0], src);
+    const float gy = __shfl_sync(FULL, t.y[0], src), gz = __shfl_sync(FULL, t.z[0], src);
+    if (lane == r) { rd = gd; rx = gx; ry = gy; rz = gz; }
+    if (lane == src) t.pop_front();
+    last = gd;
+    ++gcount;
+  }
+  thr = (gcount == K) ? last : CUDART_INF_F;
+  t.clear();
+  if (lane < gcount) { t.d[0] = rd; t.x[0] = rx; t.y[0] = ry; t.z[0] = rz; }
+  return gcount;
+}
+
+struct KnnArgs {
+  MapDev m;
+  const float4* q;     // n world-frame query points (x,y,z,*)
+  int n;
+  float4* nbr;         // [K][n] : (x,y,z,d2) of the r-th neighbour of query i at nbr[r*n+i]
+  unsigned char* cnt;  // [n] number of neighbours found
+  float max_d2;        // max_dist^2 (INF: unbounded)
+  int* phase_stats;    // optional [4]: queries finishing in phase A / B / C, total candidate points
+};
+
+// visit every point of voxel slot `idx` (head + overflow chain)
+template <int K>
+__device__ __forceinline__ void visit_voxel(const MapDev& m, size_t idx, float qx, float qy, float qz, float lim, TopK<K>& t) {
+  float4 e = __ldg(&m.slots[idx]);
+  for (;;) {
+    const float dd = sqdist(qx, qy, qz, e.x, e.y, e.z);
+    if (dd <= lim) t.insert(dd, e.x, e.y, e.z);
+    const int c = __float_as_int(e.w);
+    if (c < 0) break;
+    e = __ldg(&m.ovf[c]);
+  }
+}
+
+// squared distance from q to the axis-aligned cell [lo,hi) per axis, shrunk by mg (conservative lower bound)
+__device__ __forceinline__ float box_mind2(float qx, float qy, float qz, float lx, float ly, float lz, float hx, float hy, float hz, float mg) {
+  const float gx = fmaxf(fmaxf(lx - qx, qx - hx) - mg, 0.f);
+  const float gy = fmaxf(fmaxf(ly - qy, qy - hy) - mg, 0.f);
+  const float gz = fmaxf(fmaxf(lz - qz, qz - hz) - mg, 0.f);
+  return gx * gx + gy * gy + gz * gz;
+}
+// squared distance from q (inside) to the nearest face of [lo,hi), shrunk by mg; 0 if outside / too close
+__device__ __forceinline__ float cover2(float qx, float qy, float qz, float lx, float ly, float lz, float hx, float hy, float hz, float mg) {
+  float c = fminf(fminf(fminf(qx - lx, hx - qx), fminf(qy - ly, hy - qy)), fminf(qz - lz, hz - qz)) - mg;
+  return c > 0.f ? c * c : 0.f;
+}
+
+// Process all blocks of one coarse cell (slot cs) with the whole warp: lane = block bit within each 32-bit half word.
+template <int K>
+__device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int lane, float qx, float qy, float qz,
+                                                 int cvx, int cvy, int cvz, bool have, float thr, float lim, float mg,
+                                                 TopK<K>& t) {
+  int ccx, ccy, ccz;
+  unpack_key(__ldg(&m.ckeys[cs]), ccx, ccy, ccz);
+  const float ds = m.ds;
+  const float bs = 4.f * ds;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const unsigned long long word = __ldg(&m.cbits[(size_t)cs * 8 + k]);
+    if (word == 0ull) continue;  // uniform
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int bit = k * 64 + h * 32 + lane;
+      if (!((word >> (h * 32 + lane)) & 1ull)) continue;
+      const int bx = ccx * 8 + (bit & 7), by = ccy * 8 + ((bit >> 3) & 7), bz = ccz * 8 + (bit >> 6);
+      const float lx = (float)bx * bs, ly = (float)by * bs, lz = (float)bz * bs;
+      const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs, ly + bs, lz + bs, mg);
+      const float bound = (have || t.d[K - 1] < CUDART_INF_F) ? fminf(thr, t.d[K - 1]) : CUDART_INF_F;
+      if (md > bound || md > lim) continue;
+      const int blk = find_block(m, pack_key(bx, by, bz));
+      if (blk < 0) continue;
+      unsigned long long mask = __ldg(&m.bmask[blk]);
+      while (mask) {
+        const int s = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
+        // voxels of the phase-A stencil were already visited
+        if (abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2) continue;
+        visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, fminf(lim, bound), t);
+      }
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
+  const MapDev& m = a.m;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const float ds = m.ds;
+  const float lim = a.max_d2;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.n; i += warps_per_grid) {
+    const float4 q4 = __ldg(&a.q[i]);
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    TopK<K> t;
+    t.clear();
+    float rd = CUDART_INF_F, rx = CUDART_NAN_F, ry = CUDART_NAN_F, rz = CUDART_NAN_F, thr = CUDART_INF_F;
+    int gcount = 0;
+    int phase = 0;
+    const float qlim = 4.0e6f * ds;
+    const bool qok = fabsf(qx) < qlim && fabsf(qy) < qlim && fabsf(qz) < qlim;
+    if (qok) {
+      const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
+      const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+      // ---------------- phase A: 5x5x5 stencil, inside the 2x2x2 blocks starting at bb
+      const int bbx = (cvx - 2) >> 2, bby = (cvy - 2) >> 2, bbz = (cvz - 2) >> 2;
+      int myblk = -1;
+      unsigned long long mymask = 0ull;
+      if (lane < 8) {
+        myblk = find_block(m, pack_key(bbx + (lane & 1), bby + ((lane >> 1) & 1), bbz + (lane >> 2)));
+        if (myblk >= 0) mymask = __ldg(&m.bmask[myblk]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int v = lane + 32 * r;
+        const bool act = v < 125;
+        const int vv = act ? v : 0;
+        const int vx = cvx + (vv % 5) - 2, vy = cvy + ((vv / 5) % 5) - 2, vz = cvz + (vv / 25) - 2;
+        const int bsel = ((vx >> 2) - bbx) + 2 * ((vy >> 2) - bby) + 4 * ((vz >> 2) - bbz);
+        const int blk = __shfl_sync(FULL, myblk, bsel);
+        const unsigned long long mask = __shfl_sync(FULL, mymask, bsel);
+        const int s = (((vz & 3) << 2) + (vy & 3)) * 4 + (vx & 3);
+        if (act && blk >= 0 && ((mask >> s) & 1ull)) visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, lim, t);
+      }
+      gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
+      float cov = cover2(qx, qy, qz, (float)(cvx - 2) * ds, (float)(cvy - 2) * ds, (float)(cvz - 2) * ds,
+                         (float)(cvx + 3) * ds, (float)(cvy + 3) * ds, (float)(cvz + 3) * ds, mg);
+      bool done = (gcount == K && thr < cov) || cov > lim;
+      if (!done) {
+        // ---------------- phase B: 3x3x3 coarse cells around the query
+        phase = 1;
+        const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+        const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
+        int mycs = -1;
+        if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
+        // nearest cells first (centre cell), so the bound tightens early
+        const unsigned present = __ballot_sync(FULL, mycs >= 0);
+        {
+          const int cs = __shfl_sync(FULL, mycs, 13);
+          if (cs >= 0) scan_coarse_cell<K>(m, cs, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
+        }
+        unsigned rest = present & ~(1u << 13);
+        while (rest) {
+          const int c = __ffs(rest) - 1;
+          rest &= rest - 1;
+          const int cs = __shfl_sync(FULL, mycs, c);
+          scan_coarse_cell<K>(m, cs, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
+        }
+        gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
+        const float cs32 = 32.f * ds;
+        cov = cover2(qx, qy, qz, (float)(qcx - 1) * cs32, (float)(qcy - 1) * cs32, (float)(qcz - 1) * cs32,
+                     (float)(qcx + 2) * cs32, (float)(qcy + 2) * cs32, (float)(qcz + 2) * cs32, mg);
+        done = (gcount == K && thr < cov) || cov > lim;
+        if (!done) {
+          // ---------------- phase C: exhaustive scan of the coarse hash with box-distance pruning
+          phase = 2;
+          const int ncs = (int)m.chash_mask + 1;
+#pragma unroll 1
+          for (int base = 0; base < ncs; base += 32) {
+            const int cs = base + lane;
+            const uint64_t ck = __ldg(&m.ckeys[cs]);
+            bool go = false;
+            if (ck != KEY_EMPTY) {
+              int cx, cy, cz;
+              unpack_key(ck, cx, cy, cz);
+              if (!(abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1)) {
+                const float md = box_mind2(qx, qy, qz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32,
+                                           (float)(cx + 1) * cs32, (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
+                go = (gcount < K || md <= thr) && md <= lim;
+              }
+            }
+            unsigned todo = __ballot_sync(FULL, go);
+            if (!todo) continue;
+            while (todo) {
+              const int c = __ffs(todo) - 1;
+              todo &= todo - 1;
+              scan_coarse_cell<K>(m, base + c, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
+            }
+            gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
+          }
+        }
+      }
+    }
+    if (lane < K) a.nbr[(size_t)lane * a.n + i] = make_float4(rx, ry, rz, rd);
+    if (lane == 0) {
+      a.cnt[i] = (unsigned char)gcount;
+      if (a.phase_stats) atomicAdd(&a.phase_stats[phase], 1);
+    }
+  }
+}
+
+// K0: body -> world transform (laserMapping.cpp:1894-1898): double math (Eigen quaternion * vector form), result
+// rounded to float.  R = s.rot, Roff = s.offset_R_L_I.
+struct PoseDev {
+  double rot[4];   // x,y,z,w
+  double offR[4];
+  double pos[3];
+  double offT[3];
+};
+__device__ __forceinline__ void qrot_d(const double* q, double vx, double vy, double vz, double& ox, double& oy, double& oz) {
+  double ux = __dsub_rn(__dmul_rn(q[1], vz), __dmul_rn(q[2], vy));
+  double uy = __dsub_rn(__dmul_rn(q[2], vx), __dmul_rn(q[0], vz));
+  double uz = __dsub_rn(__dmul_rn(q[0], vy), __dmul_rn(q[1], vx));
+  ux = __dadd_rn(ux, ux); uy = __dadd_rn(uy, uy); uz = __dadd_rn(uz, uz);
+  const double cx = __dsub_rn(__dmul_rn(q[1], uz), __dmul_rn(q[2], uy));
+  const double cy = __dsub_rn(__dmul_rn(q[2], ux), __dmul_rn(q[0], uz));
+  const double cz = __dsub_rn(__dmul_rn(q[0], uy), __dmul_rn(q[1], ux));
+  ox = __dadd_rn(__dadd_rn(vx, __dmul_rn(q[3], ux)), cx);
+  oy = __dadd_rn(__dadd_rn(vy, __dmul_rn(q[3], uy)), cy);
+  oz = __dadd_rn(__dadd_rn(vz, __dmul_rn(q[3], uz)), cz);
+}
+__device__ __forceinline__ float4 body_to_world(const PoseDev& s, const float4 pb) {
+  double ax, ay, az, gx, gy, gz;
+  qrot_d(s.offR, (double)pb.x, (double)pb.y, (double)pb.z, ax, ay, az);
+  ax = __dadd_rn(ax, s.offT[0]); ay = __dadd_rn(ay, s.offT[1]); az = __dadd_rn(az, s.offT[2]);
+  qrot_d(s.rot, ax, ay, az, gx, gy, gz);
+  return make_float4((float)__dadd_rn(gx, s.pos[0]), (float)__dadd_rn(gy, s.pos[1]), (float)__dadd_rn(gz, s.pos[2]), pb.w);
+}
+__global__ void k_transform(PoseDev s, const float4* __restrict__ body, float4* __restrict__ world, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) world[i] = body_to_world(s, body[i]);
+}
+
+}  // namespace flb

@@ -1,0 +1,111 @@
+// voxel_map.cuh — device-side layout of the hashed voxel map that replaces the reference's CPU ikd-Tree
+// (include/ikd-Tree/ikd_Tree.{h,cpp}).  sm_100a only.
+//
+// Geometry (all in float, as the reference computes its voxel boxes, ikd_Tree.cpp:424-429):
+//   voxel  v = floor(x / ds)           ds = downsample_size = filter_size_map_min
+//   block  b = v >> 2   (4x4x4 voxels, 64 head slots = 1 KB, contiguous => one bulk-copyable bucket)
+//   coarse c = b >> 3   (8x8x8 blocks; 512-bit block-occupancy bitmap) — only used to bound far searches.
+//
+// Storage in HBM
+//   keys[C]/vals[C]   open-addressing hash  block key -> block index   (C = 2^k >= 2*B, 8+4 B per entry)
+//   bmask[B]          64-bit voxel occupancy of a block
+//   slots[B*64]       float4 head point of each voxel: x,y,z and w = int index of an overflow node (-1: none).
+//                     INVARIANT: w == -1 whenever the voxel has no overflow chain (also while the voxel is empty).
+//   ovf[O]            float4 overflow nodes (x,y,z, w = next) for the rare voxels holding > 1 point
+//                     (first Build, no-downsample inserts: SURVEY.md §3.3)
+//   bkey[B]           key of each allocated block (EMPTY if free) — lets delete/flatten iterate blocks densely
+//   ckeys[CC]/cbits[CC*8]  coarse hash + bitmaps
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace flb {
+
+constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint64_t KEY_TOMB = 0xFFFFFFFFFFFFFFFEull;
+constexpr int COORD_BIAS = 1 << 20;  // 21-bit biased coordinates per axis
+
+// counters[] indices
+enum Counter : int {
+  CNT_BLK_BUMP = 0,   // next never-used block index
+  CNT_BLK_FREE,       // size of free_blk stack
+  CNT_OVF_BUMP,       // next never-used overflow node
+  CNT_OVF_FREE,       // size of free_ovf stack
+  CNT_VALID,          // number of valid points
+  CNT_KEYS_USED,      // live keys in the block hash
+  CNT_KEYS_TOMB,      // tombstones in the block hash
+  CNT_COARSE_USED,    // live coarse cells
+  CNT_ERROR,          // sticky device error flags (ERR_*)
+  CNT_SCRATCH0,       // per-call scratch (returned counts)
+  CNT_SCRATCH1,
+  CNT_SCRATCH2,
+  CNT_CMIN_X, CNT_CMIN_Y, CNT_CMIN_Z,  // coarse-cell bounding box of everything ever inserted since last rebuild
+  CNT_CMAX_X, CNT_CMAX_Y, CNT_CMAX_Z,
+  CNT_COUNT = 32
+};
+enum DevError : int { ERR_BLOCKS_FULL = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4, ERR_COARSE_FULL = 8, ERR_RANGE = 16 };
+
+struct MapDev {
+  uint64_t* keys;
+  uint32_t* vals;
+  uint64_t* bmask;
+  float4* slots;
+  float4* ovf;
+  uint64_t* bkey;
+  uint32_t* free_blk;
+  uint32_t* free_ovf;
+  uint64_t* ckeys;
+  uint64_t* cbits;
+  int* counters;
+  uint32_t hash_mask;    // C-1
+  uint32_t chash_mask;   // CC-1
+  int block_cap;         // B
+  int ovf_cap;           // O
+  float ds;              // voxel size (float, = (float)filter_size_map_min)
+};
+
+__host__ __device__ __forceinline__ uint64_t pack_key(int x, int y, int z) {
+  return ((uint64_t)(uint32_t)(x + COORD_BIAS) << 42) | ((uint64_t)(uint32_t)(y + COORD_BIAS) << 21) |
+         (uint64_t)(uint32_t)(z + COORD_BIAS);
+}
+__host__ __device__ __forceinline__ void unpack_key(uint64_t k, int& x, int& y, int& z) {
+  x = (int)((k >> 42) & 0x1FFFFF) - COORD_BIAS;
+  y = (int)((k >> 21) & 0x1FFFFF) - COORD_BIAS;
+  z = (int)(k & 0x1FFFFF) - COORD_BIAS;
+}
+__host__ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+// voxel index of a coordinate: the reference's floor(x/downsample_size) in float (ikd_Tree.cpp:424).
+__device__ __forceinline__ int voxel_of(float x, float ds) { return (int)floorf(__fdiv_rn(x, ds)); }
+
+// Block lookup (read-only). Returns block index or -1.
+__device__ __forceinline__ int find_block(const MapDev& m, uint64_t key) {
+  uint32_t s = hash_key(key) & m.hash_mask;
+  for (int probe = 0; probe <= (int)m.hash_mask; ++probe) {
+    uint64_t k = __ldg(&m.keys[s]);
+    if (k == key) return (int)__ldg(&m.vals[s]);
+    if (k == KEY_EMPTY) return -1;
+    s = (s + 1) & m.hash_mask;
+  }
+  return -1;
+}
+// Coarse-cell lookup. Returns slot index in ckeys/cbits or -1.
+__device__ __forceinline__ int find_coarse(const MapDev& m, uint64_t key) {
+  uint32_t s = hash_key(key) & m.chash_mask;
+  for (int probe = 0; probe <= (int)m.chash_mask; ++probe) {
+    uint64_t k = __ldg(&m.ckeys[s]);
+    if (k == key) return (int)s;
+    if (k == KEY_EMPTY) return -1;
+    s = (s + 1) & m.chash_mask;
+  }
+  return -1;
+}
+
+}  // namespace flb

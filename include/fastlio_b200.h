@@ -1,0 +1,190 @@
+/*
+ * fastlio_b200.h — C ABI of the B200-native FAST-LIO2 per-scan hot path.
+ *
+ * This is the drop-in boundary for the path named in BASELINE.json:north_star.  Each entry point states the
+ * reference interface it replaces (paths relative to the reference repo Yixin-F/better_fastlio2):
+ *
+ *   map object       KD_TREE<PointType> ikdtree            include/ikd-Tree/ikd_Tree.h:225-249, src/laserMapping.cpp:116
+ *   measurement pass h_share_model(state_ikfom&, dyn_share_datastruct<double>&)      src/laserMapping.cpp:1876-2004
+ *   filter update    esekf::update_iterated_dyn_share_modified(R, solve_time)
+ *                                                          include/IKFoM_toolkit/esekfom/esekfom.hpp:1620-1938
+ *   map insert       map_incremental()                     src/laserMapping.cpp:1440-1496
+ *   map delete       lasermap_fov_segment()                src/laserMapping.cpp:1136-1200
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success, non-zero on error
+ *     (never throw); flb_last_error() returns a thread-local message.  The reference has no error codes on this
+ *     path — the C++ facades in include/fastlio_b200/ map errors to valid=false / ROS_ERROR.
+ *   - Points are float xyz with a caller-given byte stride (12 for packed xyz, 16 for float4, 48 for
+ *     pcl::PointXYZINormal as used by PointType, common_lib.h:161).  Input buffers are borrowed for the call.
+ *   - All *host* pointers unless the name says "_dev".  Calls on one handle must be serialised by the caller (the
+ *     reference issues all map/search calls from the main thread); different handles are independent.
+ *   - There is NO CPU fallback: every compute entry point fails loudly if no CUDA device is usable.
+ *
+ * State layout "state26" (doubles), mirrors state_ikfom (include/use-ikfom.hpp:21-30):
+ *   [0:3) pos | [3:7) rot quaternion (x,y,z,w = Eigen coeffs order) | [7:11) offset_R_L_I (x,y,z,w) |
+ *   [11:14) offset_T_L_I | [14:17) vel | [17:20) bg | [20:23) ba | [23:26) grav (S2, |g| = 9.809)
+ * Covariance: 23x23 doubles, row-major, error-state order pos,rot,offR,offT,vel,bg,ba,grav(2).
+ */
+#ifndef FASTLIO_B200_H_
+#define FASTLIO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLB_NUM_MATCH_POINTS 5 /* NUM_MATCH_POINTS, include/common_lib.h:149 */
+#define FLB_STATE_DIM 26
+#define FLB_STATE_DOF 23
+
+typedef struct flb_map flb_map;         /* device hashed-voxel map; replaces KD_TREE<PointType> */
+typedef struct flb_session flb_session; /* per-scan measurement context; replaces h_share_model's file-scope globals */
+
+/* ------------------------------------------------------------------------------------------------ errors / device */
+const char* flb_last_error(void);
+int flb_device_count(void);          /* number of CUDA devices visible (0 => every compute call fails) */
+const char* flb_version(void);
+
+/* ------------------------------------------------------------------------------------------------ map (KD_TREE API) */
+typedef struct flb_map_config {
+  float voxel_size;        /* downsample_size / filter_size_map_min (KD_TREE ctor box_length, ikd_Tree.h:226) */
+  int max_points;          /* capacity in points (valid + overflow chains); 0 -> 8M */
+  int max_blocks;          /* capacity in 4x4x4-voxel blocks; 0 -> max_points/4 */
+  int device;              /* CUDA device ordinal */
+} flb_map_config;
+
+int flb_map_create(const flb_map_config* cfg, flb_map** out);     /* KD_TREE::KD_TREE, ikd_Tree.cpp:9-17 */
+void flb_map_destroy(flb_map* m);                                 /* KD_TREE::~KD_TREE, ikd_Tree.cpp:19-27 */
+int flb_map_set_downsample_param(flb_map* m, float voxel_size);   /* set_downsample_param, ikd_Tree.cpp:39-42
+                                                                     (only legal while the map is empty) */
+int flb_map_has_root(const flb_map* m);                           /* Root_Node != nullptr test, laserMapping.cpp:2328 */
+
+/* Build (ikd_Tree.cpp:352-364): replace contents by the cloud, inserted verbatim (no per-voxel dedupe). */
+int flb_map_build(flb_map* m, const float* xyz, int n, int stride_bytes);
+/* reconstruct (ikd_Tree.cpp:1393-1405): delete everything then Build. */
+int flb_map_reconstruct(flb_map* m, const float* xyz, int n, int stride_bytes);
+/* Add_Points (ikd_Tree.cpp:413-489). downsample_on!=0: per-voxel winner = closest to the voxel centre (sequential
+ * semantics of the reference reproduced); returns in *n_added the reference's return value (number of add ops). */
+int flb_map_add_points(flb_map* m, const float* xyz, int n, int stride_bytes, int downsample_on, int* n_added);
+/* Delete_Point_Boxes (ikd_Tree.cpp:535-556): boxes = nb x {min xyz, max xyz} (BoxPointType, ikd_Tree.h:32-35),
+ * half-open test min <= p < max (ikd_Tree.cpp:670); *n_deleted = number of points removed. */
+int flb_map_delete_boxes(flb_map* m, const float* boxes6, int nb, int* n_deleted);
+/* Delete_Points (ikd_Tree.cpp:513-533): remove points equal to the given ones within 1e-6 per axis (same_point). */
+int flb_map_delete_points(flb_map* m, const float* xyz, int n, int stride_bytes, int* n_deleted);
+/* Nearest_Search (ikd_Tree.cpp:366-397), batched over nq queries: exact k-NN (k <= 5 on the fast path, <= 20
+ * otherwise) among valid points with float squared distances, ascending; max_dist <= 0 means unbounded (the
+ * reference default INFINITY).  out_xyz[nq*k*3], out_d2[nq*k] (unfilled = NaN / INF), out_cnt[nq]. */
+int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, int stride_bytes, int k, float max_dist,
+                           float* out_xyz, float* out_d2, int* out_cnt);
+/* Box_Search (ikd_Tree.cpp:399-404) / Radius_Search (:406-411): points in a half-open box / within radius.
+ * Writes up to cap points; *n_found is the total. */
+int flb_map_box_search(flb_map* m, const float* box6, float* out_xyz, int cap, int* n_found);
+int flb_map_radius_search(flb_map* m, const float* center_xyz, float radius, float* out_xyz, int cap, int* n_found);
+int flb_map_validnum(flb_map* m);  /* validnum(), ikd_Tree.cpp:128-145 ; -1 on error */
+int flb_map_size(flb_map* m);      /* size(), ikd_Tree.cpp:78-96 (== validnum here: no lazy tombstones) */
+/* flatten (ikd_Tree.cpp:1325-1352): all valid points, arbitrary order. Writes up to cap; *n = total valid. */
+int flb_map_flatten(flb_map* m, float* out_xyz, int cap, int* n);
+/* tree_range (ikd_Tree.h:245): bounding box of valid points {min xyz, max xyz}. */
+int flb_map_range(flb_map* m, float* box6);
+
+typedef struct flb_map_stats {
+  int valid_points, blocks_in_use, block_capacity, overflow_in_use, overflow_capacity;
+  int hash_capacity, hash_tombstones, coarse_cells, rehash_count;
+  size_t device_bytes;
+} flb_map_stats;
+int flb_map_get_stats(flb_map* m, flb_map_stats* out);
+
+/* ------------------------------------------------------------------------------------------------ session (per scan) */
+typedef struct flb_session_config {
+  int max_scan_points;      /* capacity N of feats_down_body (the reference caps at 100000, laserMapping.cpp:52) */
+  int extrinsic_est_en;     /* mapping/extrinsic_est_en, laserMapping.cpp:44 */
+  int max_iterations;       /* NUM_MAX_ITERATIONS (ikdtree/max_iteration), laserMapping.cpp:2064 */
+  double laser_point_cov;   /* LASER_POINT_COV, laserMapping.cpp:14 (0.001) */
+  double filter_size_map_min; /* ikdtree/filter_size_map_min as the DOUBLE the caller holds, laserMapping.cpp:56 */
+  double limit[FLB_STATE_DOF]; /* epsi, laserMapping.cpp:2148-2149 (0.001 each) */
+} flb_session_config;
+
+void flb_session_default_config(flb_session_config* cfg);
+int flb_session_create(flb_map* m, const flb_session_config* cfg, flb_session** out);
+void flb_session_destroy(flb_session* s);
+
+/* feats_down_body (laserMapping.cpp:2322-2325): upload the voxel-downsampled, undistorted scan (LiDAR frame).
+ * Resets the per-scan caches (Nearest_Points, point_selected_surf := true, laserMapping.cpp:2131). */
+int flb_scan_upload(flb_session* s, const float* body_xyz, int n, int stride_bytes);
+/* Same, when the scan already lives in device memory as n float4 (x,y,z,*) on the session's device. */
+int flb_scan_set_device(flb_session* s, const void* body_xyz4_dev, int n);
+
+typedef struct flb_pass_result {
+  int valid;               /* ekfom_data.valid (false when effct_feat_num < 1, laserMapping.cpp:1956-1961) */
+  int effct_feat_num;      /* M */
+  double total_residual;   /* sum |pd2|, laserMapping.cpp:1951 */
+  double HTH[144];         /* h_x^T h_x, 12x12 row-major (esekfom.hpp:1790) */
+  double HTh[12];          /* h_x^T h */
+} flb_pass_result;
+
+/* One h_share_model call (laserMapping.cpp:1876-2004) for the iterate `state26`; search != 0 == ekfom_data.converge
+ * (re-run the 5-NN), else the cached Nearest_Points / point_selected_surf are reused.  Returns the reduced normal
+ * equations (boundary B3 of SURVEY.md §8b). */
+int flb_pass(flb_session* s, const double* state26, int search, flb_pass_result* out);
+/* Exact rows of the last flb_pass (boundary B1): h_x as M x 12 COLUMN-major doubles (Eigen::MatrixXd layout,
+ * esekfom.hpp:82) with leading dimension ld >= M, and h[M] (= -pd2, laserMapping.cpp:2001). */
+int flb_pass_rows(flb_session* s, double* h_x_colmajor, int ld, double* h, int capacity_rows, int* M);
+
+typedef struct flb_update_stats {
+  int passes, search_passes, effct_feat_num, converged_count;
+  double total_residual;
+  float gpu_ms;            /* CUDA-event time of all kernels of this update */
+} flb_update_stats;
+
+/* update_iterated_dyn_share_modified (esekfom.hpp:1620-1938) with the built-in measurement model: state26 / P23x23
+ * hold the propagated state in and the posterior out. */
+int flb_esikf_update(flb_session* s, double* state26, double* P, flb_update_stats* stats);
+
+/* map_incremental (laserMapping.cpp:1440-1496) with the posterior state: classify every scan point with the cached
+ * neighbours, then Add_Points(PointToAdd,true) and Add_Points(PointNoNeedDownsample,false). */
+int flb_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, int* n_to_add, int* n_no_downsample);
+
+/* Debug / parity: the per-scan caches. Any pointer may be NULL. nbr_xyz[N*5*3], nbr_d2[N*5], nbr_cnt[N],
+ * selected[N] (point_selected_surf), normvec[N*4] (nx,ny,nz,pd2), world_xyz[N*3] (feats_down_world). */
+int flb_neighbors_download(flb_session* s, float* nbr_xyz, float* nbr_d2, int* nbr_cnt, unsigned char* selected,
+                           float* normvec, float* world_xyz);
+
+/* ------------------------------------------------------------------------------------------------ fov segment (host) */
+typedef struct flb_fov_state {
+  float local_map_min[3], local_map_max[3]; /* LocalMap_Points, laserMapping.cpp:1132 */
+  int initialized;                          /* Localmap_Initialized, :1133 */
+  double cube_len;                          /* mapping/cube_len */
+  float det_range;                          /* mapping/det_range (DET_RANGE) */
+  double pos_lid[3];                        /* pos_lid, laserMapping.cpp:2383 — LiDAR position of the PREVIOUS
+                                               posterior (zero before the first update, as the reference's
+                                               zero-initialised global); maintained by flb_scan_step */
+} flb_fov_state;
+/* lasermap_fov_segment (laserMapping.cpp:1136-1200): moves the local-map cube and deletes the slabs that left it.
+ * pos_lid = LiDAR position in world. *n_boxes (<=3) / *n_deleted = kdtree_delete_counter. */
+int flb_fov_segment(flb_map* m, flb_fov_state* fov, const double* pos_lid, float* boxes_out18, int* n_boxes,
+                    int* n_deleted);
+
+/* ------------------------------------------------------------------------------------------------ whole per-scan step */
+typedef struct flb_scan_result {
+  flb_update_stats update;
+  int n_to_add, n_no_downsample, n_deleted, map_valid;
+  float gpu_ms_total;      /* update + insert + delete kernels, CUDA events on the session stream */
+  int kernel_launches;     /* number of kernels launched by this step */
+} flb_scan_result;
+/* The timed region of SURVEY.md §8d: lasermap_fov_segment -> update_iterated_dyn_share_modified -> map_incremental
+ * (laserMapping.cpp:2320, :2380, :2401) for one scan.  body may be NULL if the scan was already set with
+ * flb_scan_upload / flb_scan_set_device.  fov may be NULL to skip the fov segment. */
+int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body_xyz, int n, int stride_bytes, double* state26,
+                  double* P, int flg_EKF_inited, flb_scan_result* out);
+
+/* Stream access for callers that overlap work (returns a cudaStream_t as void*). */
+void* flb_session_stream(flb_session* s);
+int flb_session_sync(flb_session* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTLIO_B200_H_ */
