@@ -67,7 +67,9 @@ int flb_map_build(flb_map* m, const float* xyz, int n, int stride_bytes);
 /* reconstruct (ikd_Tree.cpp:1393-1405): delete everything then Build. */
 int flb_map_reconstruct(flb_map* m, const float* xyz, int n, int stride_bytes);
 /* Add_Points (ikd_Tree.cpp:413-489). downsample_on!=0: per-voxel winner = closest to the voxel centre (sequential
- * semantics of the reference reproduced); returns in *n_added the reference's return value (number of add ops). */
+ * semantics of the reference reproduced for the resulting map).  *n_added = number of voxels whose content changed
+ * (the reference returns the number of sequential add operations, which its caller overwrites without reading,
+ * laserMapping.cpp:1492-1494; the two differ only when several new points fall into one voxel). */
 int flb_map_add_points(flb_map* m, const float* xyz, int n, int stride_bytes, int downsample_on, int* n_added);
 /* Delete_Point_Boxes (ikd_Tree.cpp:535-556): boxes = nb x {min xyz, max xyz} (BoxPointType, ikd_Tree.h:32-35),
  * half-open test min <= p < max (ikd_Tree.cpp:670); *n_deleted = number of points removed. */
