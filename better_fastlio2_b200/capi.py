@@ -56,6 +56,12 @@ class ScanResult(C.Structure):
                 ("map_valid", C.c_int), ("gpu_ms_total", C.c_float), ("kernel_launches", C.c_int)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int * 8), ("regions", C.c_int * 8), ("knn_phase", C.c_longlong * 4)]
+
+
+K_CLASSES = ["transform", "knn", "residual", "reduce", "classify", "insert", "delete"]
+
 _lib = None
 
 # every symbol include/fastlio_b200.h declares
@@ -67,6 +73,7 @@ EXPORTS = [
     "flb_map_get_stats", "flb_session_default_config", "flb_session_create", "flb_session_destroy", "flb_scan_upload",
     "flb_scan_set_device", "flb_pass", "flb_pass_rows", "flb_esikf_update", "flb_map_incremental",
     "flb_neighbors_download", "flb_fov_segment", "flb_scan_step", "flb_session_stream", "flb_session_sync",
+    "flb_map_profile_enable", "flb_map_profile_read",
 ]
 
 
@@ -116,6 +123,8 @@ def lib():
         L.flb_session_stream.argtypes = [vp]
         L.flb_session_stream.restype = vp
         L.flb_session_sync.argtypes = [vp]
+        L.flb_map_profile_enable.argtypes = [vp, C.c_int]
+        L.flb_map_profile_read.argtypes = [vp, C.POINTER(Profile), C.c_int]
         _lib = L
     return _lib
 
@@ -235,6 +244,18 @@ class KDTree:
         _chk(lib().flb_map_range(self.h, _p(b)))
         return b
 
+    def profile_enable(self, on=True):
+        _chk(lib().flb_map_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        p = Profile()
+        _chk(lib().flb_map_profile_read(self.h, C.byref(p), 1 if reset else 0))
+        out = {}
+        for i, k in enumerate(K_CLASSES):
+            out[k] = {"ms": p.ms[i], "launches": p.launches[i], "regions": p.regions[i]}
+        out["knn_phase"] = [int(p.knn_phase[i]) for i in range(4)]
+        return out
+
     def stats(self):
         s = MapStats()
         _chk(lib().flb_map_get_stats(self.h, C.byref(s)))
@@ -334,6 +355,17 @@ class Session:
             _chk(lib().flb_scan_step(self.h, C.byref(fov) if fov is not None else None, None, 0, 0, _p(st), _p(Pm),
                                      1 if flg_EKF_inited else 0, C.byref(r)))
         return st, Pm, r
+
+    def scan_step_ptr(self, fov, ptr, n, stride, state26, P, flg_EKF_inited=True):
+        """flb_scan_step on a raw host pointer (e.g. pinned memory owned by the caller); state26/P updated in place."""
+        r = ScanResult()
+        self.n = int(n) if ptr else self.n
+        _chk(lib().flb_scan_step(self.h, C.byref(fov) if fov is not None else None, C.c_void_p(ptr) if ptr else None,
+                                 int(n), int(stride), _p(state26), _p(P), 1 if flg_EKF_inited else 0, C.byref(r)))
+        return r
+
+    def stream_ptr(self):
+        return lib().flb_session_stream(self.h)
 
     def sync(self):
         _chk(lib().flb_session_sync(self.h))

@@ -76,6 +76,30 @@ struct flb_map {
   int* h_counters = nullptr;     // pinned mirror of counters
   int* d_misc = nullptr;         // misc device ints (out counts, range)
   int launches = 0;              // kernel launch counter (cumulative)
+  // optional per-kernel-class CUDA-event timing (flb_map_profile_*)
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int cls; int nlaunch; };
+  std::vector<ProfRec> prof_pool;
+  size_t prof_used = 0;
+  int* d_phase = nullptr;        // k-NN phase histogram (device, 4 ints)
+  int* worklist = nullptr;       // unresolved-query list of the stencil k-NN kernel
+  int work_cap = 0;
+};
+
+struct ProfScope {
+  flb_map* m; flb_map::ProfRec* r = nullptr; int l0;
+  ProfScope(flb_map* m_, int cls) : m(m_), l0(m_->launches) {
+    if (!m->prof_on) return;
+    if (m->prof_used == m->prof_pool.size()) {
+      flb_map::ProfRec n{};
+      if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
+      m->prof_pool.push_back(n);
+    }
+    r = &m->prof_pool[m->prof_used++];
+    r->cls = cls;
+    cudaEventRecord(r->a, m->stream);
+  }
+  ~ProfScope() { if (r) { r->nlaunch = m->launches - l0; cudaEventRecord(r->b, m->stream); } }
 };
 
 static int dev_alloc(flb_map* m, void** p, size_t bytes) {
@@ -87,8 +111,7 @@ static int dev_alloc(flb_map* m, void** p, size_t bytes) {
 static int map_reset_storage(flb_map* m) {
   MapDev& d = m->d;
   cudaStream_t st = m->stream;
-  CU(cudaMemsetAsync(d.keys, 0xFF, sizeof(uint64_t) * m->hash_cap, st));
-  CU(cudaMemsetAsync(d.vals, 0xFF, sizeof(uint32_t) * m->hash_cap, st));
+  CU(cudaMemsetAsync(d.hent, 0xFF, sizeof(HEntry) * m->hash_cap, st));
   CU(cudaMemsetAsync(d.bmask, 0, sizeof(uint64_t) * d.block_cap, st));
   CU(cudaMemsetAsync(d.slots, 0xFF, sizeof(float4) * 64 * (size_t)d.block_cap, st));
   CU(cudaMemsetAsync(d.bkey, 0xFF, sizeof(uint64_t) * d.block_cap, st));
@@ -142,8 +165,7 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   d.hash_mask = m->hash_cap - 1;
   d.chash_mask = m->chash_cap - 1;
   int rc = 0;
-  rc |= dev_alloc(m, (void**)&d.keys, sizeof(uint64_t) * m->hash_cap);
-  rc |= dev_alloc(m, (void**)&d.vals, sizeof(uint32_t) * m->hash_cap);
+  rc |= dev_alloc(m, (void**)&d.hent, sizeof(HEntry) * m->hash_cap);
   rc |= dev_alloc(m, (void**)&d.bmask, sizeof(uint64_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.slots, sizeof(float4) * 64 * (size_t)d.block_cap);
   rc |= dev_alloc(m, (void**)&d.ovf, sizeof(float4) * (size_t)d.ovf_cap);
@@ -154,6 +176,7 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   rc |= dev_alloc(m, (void**)&d.cbits, sizeof(uint64_t) * 8 * (size_t)m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.counters, sizeof(int) * CNT_COUNT);
   rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 16);
+  rc |= dev_alloc(m, (void**)&m->d_phase, sizeof(int) * 4);
   if (rc) { flb_map_destroy(m); return 1; }
   if (cudaMallocHost((void**)&m->h_counters, sizeof(int) * CNT_COUNT) != cudaSuccess) { flb_map_destroy(m); return set_err("cudaMallocHost failed"); }
   // triangle index tables of the 13x13 augmented normal equations
@@ -172,10 +195,11 @@ extern "C" void flb_map_destroy(flb_map* m) {
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   MapDev& d = m->d;
-  void* ptrs[] = {d.keys, d.vals, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
-                  m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf};
+  void* ptrs[] = {d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
+                  m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_counters) cudaFreeHost(m->h_counters);
+  for (auto& r : m->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -248,6 +272,7 @@ static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls
   const int g = grid_for(n, 256, m->sm_count * 8);
   cudaStream_t st = m->stream;
   const unsigned char* c = (mode == 2) ? cls : nullptr;
+  ProfScope ps(m, FLB_K_INSERT);
   k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n);
   m->launches++;
   if (mode == 1 || mode == 2) {
@@ -327,8 +352,11 @@ static int delete_common(flb_map* m, const float* params, int np, int floats_per
   if (upload_params(m, params, np * floats_per)) return 1;
   if (zero_scratch_counters(m)) return 1;
   const int g = grid_for(nblk * 32, 256, m->sm_count * 8);
-  k_delete<<<g, 256, 0, m->stream>>>(m->d, m->dparams, np, mode, nblk);
-  m->launches++;
+  {
+    ProfScope ps(m, FLB_K_DELETE);
+    k_delete<<<g, 256, 0, m->stream>>>(m->d, m->dparams, np, mode, nblk);
+    m->launches++;
+  }
   CU(cudaGetLastError());
   if (fetch_counters(m)) return 1;
   if (n_deleted) *n_deleted = m->h_counters[CNT_SCRATCH0];
@@ -356,8 +384,7 @@ static int maybe_rehash(flb_map* m) {
   if (m->h_counters[CNT_KEYS_TOMB] <= (int)(m->hash_cap / 8)) return 0;
   const int nblk = blocks_bumped(m);
   cudaStream_t st = m->stream;
-  CU(cudaMemsetAsync(m->d.keys, 0xFF, sizeof(uint64_t) * m->hash_cap, st));
-  CU(cudaMemsetAsync(m->d.vals, 0xFF, sizeof(uint32_t) * m->hash_cap, st));
+  CU(cudaMemsetAsync(m->d.hent, 0xFF, sizeof(HEntry) * m->hash_cap, st));
   CU(cudaMemsetAsync(m->d.ckeys, 0xFF, sizeof(uint64_t) * m->chash_cap, st));
   CU(cudaMemsetAsync(m->d.cbits, 0, sizeof(uint64_t) * 8 * (size_t)m->chash_cap, st));
   int init[8] = {0, 0, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
@@ -373,11 +400,24 @@ static int maybe_rehash(flb_map* m) {
   return fetch_counters(m);
 }
 
+// k-NN = thread-per-query stencil kernel + exact warp-per-query kernel over the (small) unresolved work list.
 template <int K>
-static void launch_knn(flb_map* m, const KnnArgs& a) {
-  const int g = grid_for(a.n * 32, 128, m->sm_count * 16);
-  k_knn<K><<<g, 128, 0, m->stream>>>(a);
-  m->launches++;
+static int launch_knn(flb_map* m, KnnArgs a) {
+  if (a.n > m->work_cap) {
+    if (m->worklist) cudaFree(m->worklist);
+    m->worklist = nullptr; m->work_cap = 0;
+    const int cap = std::max(a.n, 1 << 17);
+    CU(cudaMalloc((void**)&m->worklist, sizeof(int) * (size_t)cap));
+    m->work_cap = cap;
+  }
+  a.worklist = m->worklist;
+  a.work_count = m->d_misc + 12;
+  CU(cudaMemsetAsync(a.work_count, 0, sizeof(int), m->stream));
+  k_knn_stencil<K><<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+  // the fallback grid is sized for the typical <2 % unresolved share; it loops over the list
+  k_knn<K><<<m->sm_count * 4, 128, 0, m->stream>>>(a);
+  m->launches += 2;
+  return 0;
 }
 
 static int ensure_outbuf(flb_map* m, int n) {
@@ -406,8 +446,8 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
   a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt;
   a.max_d2 = (max_dist > 0.f && max_dist < 1e18f) ? max_dist * max_dist : INFINITY;
   a.phase_stats = nullptr;
-  if (K == 5) launch_knn<5>(m, a); else launch_knn<20>(m, a);
-  cudaError_t le = cudaGetLastError();
+  int lrc = (K == 5) ? launch_knn<5>(m, a) : launch_knn<20>(m, a);
+  cudaError_t le = lrc ? cudaErrorUnknown : cudaGetLastError();
   std::vector<float4> h((size_t)nq * K);
   std::vector<unsigned char> hc(nq);
   if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), m->outbuf, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost, m->stream);
@@ -518,6 +558,33 @@ extern "C" int flb_map_get_stats(flb_map* m, flb_map_stats* out) {
   out->coarse_cells = c[CNT_COARSE_USED];
   out->rehash_count = m->rehash_count;
   out->device_bytes = m->device_bytes;
+  return 0;
+}
+
+extern "C" int flb_map_profile_enable(flb_map* m, int on) {
+  if (!m) return set_err("null map");
+  CU(cudaSetDevice(m->cfg.device));
+  CU(cudaStreamSynchronize(m->stream));
+  m->prof_on = on != 0;
+  m->prof_used = 0;
+  CU(cudaMemsetAsync(m->d_phase, 0, sizeof(int) * 4, m->stream));
+  return 0;
+}
+extern "C" int flb_map_profile_read(flb_map* m, flb_profile* out, int reset) {
+  if (!m || !out) return set_err("null argument");
+  CU(cudaSetDevice(m->cfg.device));
+  CU(cudaStreamSynchronize(m->stream));
+  memset(out, 0, sizeof(*out));
+  for (size_t i = 0; i < m->prof_used; ++i) {
+    const auto& r = m->prof_pool[i];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    if (r.cls >= 0 && r.cls < FLB_K_COUNT) { out->ms[r.cls] += ms; out->launches[r.cls] += r.nlaunch; out->regions[r.cls] += 1; }
+  }
+  int ph[4];
+  CU(cudaMemcpy(ph, m->d_phase, sizeof(ph), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out->knn_phase[i] = ph[i];
+  if (reset) { m->prof_used = 0; CU(cudaMemset(m->d_phase, 0, sizeof(int) * 4)); }
   return 0;
 }
 
@@ -685,18 +752,30 @@ static int enqueue_pass(flb_session* s, const double* state26, int search) {
   const int n = s->n;
   const PoseDev pose = pose_from(state26);
   s->last_pose = pose;
-  k_transform<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->world, n);
-  m->launches++;
+  {
+    ProfScope ps(m, FLB_K_TRANSFORM);
+    k_transform<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->world, n);
+    m->launches++;
+  }
   if (search) {
+    ProfScope ps(m, FLB_K_KNN);
     KnnArgs a;
-    a.m = m->d; a.q = s->world; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY; a.phase_stats = nullptr;
-    launch_knn<5>(m, a);
+    a.m = m->d; a.q = s->world; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
+    a.phase_stats = m->prof_on ? m->d_phase : nullptr;
+    if (launch_knn<5>(m, a)) return 1;
   }
   const MeasArgs ma = meas_args(s, pose, search);
-  if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
-  else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
-  k_reduce_final<<<1, 384, 0, st>>>(s->partial, s->res_grid, s->dout);
-  m->launches += 2;
+  {
+    ProfScope ps(m, FLB_K_RESIDUAL);
+    if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+    else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+    m->launches++;
+  }
+  {
+    ProfScope ps(m, FLB_K_REDUCE);
+    k_reduce_final<<<1, 384, 0, st>>>(s->partial, s->res_grid, s->dout);
+    m->launches++;
+  }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(s->h_out, s->dout, sizeof(double) * NACC, cudaMemcpyDeviceToHost, st));
   s->have_pass = true;
@@ -827,9 +906,12 @@ static int enqueue_map_incremental(flb_session* s, const double* state26, int fl
   if (n <= 0) return 0;
   const PoseDev pose = pose_from(state26);
   CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
-  k_classify<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->nbr, s->cnt, n, flg_EKF_inited,
-                                                                s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
-  m->launches++;
+  {
+    ProfScope ps(m, FLB_K_CLASSIFY);
+    k_classify<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->nbr, s->cnt, n, flg_EKF_inited,
+                                                                  s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
+    m->launches++;
+  }
   CU(cudaGetLastError());
   if (insert_device(m, s->world, s->cls, n, 2)) return 1;
   CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));

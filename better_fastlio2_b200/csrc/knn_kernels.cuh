@@ -104,6 +104,8 @@ struct KnnArgs {
   unsigned char* cnt;  // [n] number of neighbours found
   float max_d2;        // max_dist^2 (INF: unbounded)
   int* phase_stats;    // optional [4]: queries finishing in phase A / B / C, total candidate points
+  int* worklist;       // stencil kernel: indices of queries it could not prove complete; warp kernel: its input list
+  int* work_count;     // number of entries in worklist (device)
 };
 
 // visit every point of voxel slot `idx` (head + overflow chain)
@@ -137,6 +139,7 @@ template <int K>
 __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int lane, float qx, float qy, float qz,
                                                  int cvx, int cvy, int cvz, bool have, float thr, float lim, float mg,
                                                  TopK<K>& t) {
+  const int qbx_ = cvx >> 2, qby_ = cvy >> 2, qbz_ = cvz >> 2;
   int ccx, ccy, ccz;
   unpack_key(__ldg(&m.ckeys[cs]), ccx, ccy, ccz);
   const float ds = m.ds;
@@ -150,6 +153,7 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
       const int bit = k * 64 + h * 32 + lane;
       if (!((word >> (h * 32 + lane)) & 1ull)) continue;
       const int bx = ccx * 8 + (bit & 7), by = ccy * 8 + ((bit >> 3) & 7), bz = ccz * 8 + (bit >> 6);
+      if (abs(bx - qbx_) <= 1 && abs(by - qby_) <= 1 && abs(bz - qbz_) <= 1) continue;  // visited by phase B0
       const float lx = (float)bx * bs, ly = (float)by * bs, lz = (float)bz * bs;
       const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs, ly + bs, lz + bs, mg);
       const float bound = (have || t.d[K - 1] < CUDART_INF_F) ? fminf(thr, t.d[K - 1]) : CUDART_INF_F;
@@ -160,9 +164,6 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
       while (mask) {
         const int s = __ffsll((long long)mask) - 1;
         mask &= mask - 1;
-        const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
-        // voxels of the phase-A stencil were already visited
-        if (abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2) continue;
         visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, fminf(lim, bound), t);
       }
     }
@@ -176,7 +177,9 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   const float ds = m.ds;
   const float lim = a.max_d2;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.n; i += warps_per_grid) {
+  const int nwork = a.worklist ? *a.work_count : a.n;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwork; w += warps_per_grid) {
+    const int i = a.worklist ? a.worklist[w] : w;
     const float4 q4 = __ldg(&a.q[i]);
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     TopK<K> t;
@@ -213,10 +216,34 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
       float cov = cover2(qx, qy, qz, (float)(cvx - 2) * ds, (float)(cvy - 2) * ds, (float)(cvz - 2) * ds,
                          (float)(cvx + 3) * ds, (float)(cvy + 3) * ds, (float)(cvz + 3) * ds, mg);
       bool done = (gcount == K && thr < cov) || cov > lim;
+      const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
       if (!done) {
-        // ---------------- phase B: 3x3x3 coarse cells around the query
+        // ---------------- phase B0: the 3x3x3 BLOCKS around the query block (one block per lane): covers >= 4 voxels
+        // around the query, enough for almost every query the stencil could not settle, and gives phase B a finite bound
         phase = 1;
-        const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+        if (lane < 27) {
+          const int bx = qbx + (lane % 3) - 1, by = qby + ((lane / 3) % 3) - 1, bz = qbz + (lane / 9) - 1;
+          const int blk = find_block(m, pack_key(bx, by, bz));
+          if (blk >= 0) {
+            unsigned long long mask = __ldg(&m.bmask[blk]);
+            while (mask) {
+              const int s = __ffsll((long long)mask) - 1;
+              mask &= mask - 1;
+              const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
+              if (abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2) continue;  // stencil: done in A
+              visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, fminf(lim, fminf(thr, t.d[K - 1])), t);
+            }
+          }
+        }
+        gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
+        const float bs4 = 4.f * ds;
+        cov = cover2(qx, qy, qz, (float)(qbx - 1) * bs4, (float)(qby - 1) * bs4, (float)(qbz - 1) * bs4,
+                     (float)(qbx + 2) * bs4, (float)(qby + 2) * bs4, (float)(qbz + 2) * bs4, mg);
+        done = (gcount == K && thr < cov) || cov > lim;
+      }
+      if (!done) {
+        // ---------------- phase B: 3x3x3 coarse cells around the query (blocks of B0 are skipped inside)
+        phase = 2;
         const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
         int mycs = -1;
         if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
         done = (gcount == K && thr < cov) || cov > lim;
         if (!done) {
           // ---------------- phase C: exhaustive scan of the coarse hash with box-distance pruning
-          phase = 2;
+          phase = 3;
           const int ncs = (int)m.chash_mask + 1;
 #pragma unroll 1
           for (int base = 0; base < ncs; base += 32) {
@@ -273,6 +300,127 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
       a.cnt[i] = (unsigned char)gcount;
       if (a.phase_stats) atomicAdd(&a.phase_stats[phase], 1);
     }
+  }
+}
+
+// K1a: phase A with ONE THREAD per query (the common case: >99 % of LiDAR returns lie on mapped surfaces and are
+// resolved by the 5x5x5 stencil).  Per query: 8 block probes (one 16-B hash entry + one 8-B occupancy word each),
+// then ONE loop over the occupied stencil voxels of all 8 blocks (per-thread cursor, so a warp iterates
+// max-over-lanes of the candidate COUNT, not the sum of per-block maxima) with one 16-B point load per candidate and
+// a branch-free insertion into a register-resident (distance, slot-id) top-K.  No cross-lane traffic.
+// Queries whose stencil cannot prove completeness — or that see an exact float distance tie, whose canonical
+// (x,y,z) order is resolved by the warp kernel — are appended to a work list for the exact kernel k_knn.
+template <int K>
+struct TopKId {
+  float d[K];
+  unsigned id[K];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int j = 0; j < K; ++j) { d[j] = CUDART_INF_F; id[j] = 0u; }
+  }
+  // branch-free sorted insert; returns true if dd equals a kept distance (tie)
+  __device__ __forceinline__ bool insert(float dd, unsigned pid) {
+    bool c[K];
+    bool tie = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) { c[j] = dd < d[j]; tie |= (dd == d[j]); }
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+      d[j] = c[j - 1] ? d[j - 1] : (c[j] ? dd : d[j]);
+      id[j] = c[j - 1] ? id[j - 1] : (c[j] ? pid : id[j]);
+    }
+    d[0] = c[0] ? dd : d[0];
+    id[0] = c[0] ? pid : id[0];
+    return tie;
+  }
+};
+
+constexpr int STENCIL_THREADS = 128;
+
+template <int K>
+__global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
+  __shared__ int s_blk[8][STENCIL_THREADS];
+  __shared__ unsigned long long s_cand[8][STENCIL_THREADS];
+  const MapDev& m = a.m;
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + tid;
+  if (i >= a.n) return;
+  const float ds = m.ds;
+  const float lim = a.max_d2;
+  const float4 q4 = __ldg(&a.q[i]);
+  const float qx = q4.x, qy = q4.y, qz = q4.z;
+  const float qlim = 4.0e6f * ds;
+  TopKId<K> t;
+  t.clear();
+  bool done = false, tie = false;
+  if (fabsf(qx) < qlim && fabsf(qy) < qlim && fabsf(qz) < qlim) {
+    const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
+    const int bbx = (cvx - 2) >> 2, bby = (cvy - 2) >> 2, bbz = (cvz - 2) >> 2;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int bx = bbx + (b & 1), by = bby + ((b >> 1) & 1), bz = bbz + (b >> 2);
+      // stencil range inside this block, per axis (local voxel coordinates 0..3); never empty for these 8 blocks
+      const int x0 = max(cvx - 2, bx * 4) - bx * 4, x1 = min(cvx + 2, bx * 4 + 3) - bx * 4;
+      const int y0 = max(cvy - 2, by * 4) - by * 4, y1 = min(cvy + 2, by * 4 + 3) - by * 4;
+      const int z0 = max(cvz - 2, bz * 4) - bz * 4, z1 = min(cvz + 2, bz * 4 + 3) - bz * 4;
+      const int blk = find_block(m, pack_key(bx, by, bz));
+      unsigned long long cand = 0ull;
+      if (blk >= 0) {
+        const unsigned xm = ((1u << (x1 - x0 + 1)) - 1u) << x0;
+        const unsigned ym = ((1u << (y1 - y0 + 1)) - 1u) << y0;
+        const unsigned zm = ((1u << (z1 - z0 + 1)) - 1u) << z0;
+        const unsigned ysp = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);  // bits 0,4,8,12
+        const unsigned long long zsp = (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) |
+                                       ((unsigned long long)(zm & 4u) << 30) | ((unsigned long long)(zm & 8u) << 45);
+        cand = __ldg(&m.bmask[blk]) & ((unsigned long long)(xm * ysp) * zsp);
+      }
+      s_blk[b][tid] = blk;
+      s_cand[b][tid] = cand;
+    }
+    // one loop over all candidates of this thread (own smem column: no synchronisation needed)
+    int b = -1, blk = 0;
+    unsigned long long cand = 0ull;
+    for (;;) {
+      while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; blk = s_blk[b][tid]; }
+      if (cand == 0ull) break;
+      const int s = __ffsll((long long)cand) - 1;
+      cand &= cand - 1;
+      const unsigned pid = (unsigned)blk * 64u + (unsigned)s;
+      float4 e = __ldg(&m.slots[pid]);
+      float dd = sqdist(qx, qy, qz, e.x, e.y, e.z);
+      if (dd <= lim) tie |= t.insert(dd, pid);
+      int c = __float_as_int(e.w);
+      while (c >= 0) {  // overflow chain of this voxel (rare)
+        e = __ldg(&m.ovf[c]);
+        dd = sqdist(qx, qy, qz, e.x, e.y, e.z);
+        if (dd <= lim) tie |= t.insert(dd, 0x80000000u | (unsigned)c);
+        c = __float_as_int(e.w);
+      }
+    }
+    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+    const float cov = cover2(qx, qy, qz, (float)(cvx - 2) * ds, (float)(cvy - 2) * ds, (float)(cvz - 2) * ds,
+                             (float)(cvx + 3) * ds, (float)(cvy + 3) * ds, (float)(cvz + 3) * ds, mg);
+    done = ((t.d[K - 1] < CUDART_INF_F && t.d[K - 1] < cov) || cov > lim) && !tie;
+  } else {
+    done = true;  // unrepresentable / NaN query: no neighbours
+  }
+  if (done) {
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const bool ok = t.d[r] < CUDART_INF_F;
+      c += ok ? 1 : 0;
+      float4 o = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_INF_F);
+      if (ok) {
+        const float4 e = (t.id[r] & 0x80000000u) ? __ldg(&m.ovf[t.id[r] & 0x7FFFFFFFu]) : __ldg(&m.slots[t.id[r]]);
+        o = make_float4(e.x, e.y, e.z, t.d[r]);
+      }
+      a.nbr[(size_t)r * a.n + i] = o;
+    }
+    a.cnt[i] = (unsigned char)c;
+    if (a.phase_stats) atomicAdd(&a.phase_stats[0], 1);
+  } else {
+    a.worklist[atomicAdd(a.work_count, 1)] = i;
   }
 }
 

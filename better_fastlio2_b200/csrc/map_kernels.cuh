@@ -91,13 +91,13 @@ __device__ __forceinline__ void coarse_clear(const MapDev& m, int bx, int by, in
 __device__ __forceinline__ void touch_block(const MapDev& m, uint64_t key, int bx, int by, int bz) {
   uint32_t s = hash_key(key) & m.hash_mask;
   for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
-    uint64_t k = *((volatile uint64_t*)&m.keys[s]);
+    uint64_t k = *((volatile uint64_t*)&m.hent[s].key);
     if (k == key) return;
     if (k == KEY_EMPTY) {
-      uint64_t old = atomicCAS((unsigned long long*)&m.keys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+      uint64_t old = atomicCAS((unsigned long long*)&m.hent[s].key, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
       if (old == KEY_EMPTY) {
         int blk = alloc_block(m);
-        m.vals[s] = (uint32_t)blk;  // -1 on exhaustion (sticky error already raised)
+        m.hent[s].val = (uint32_t)blk;  // -1 on exhaustion (sticky error already raised)
         if (blk >= 0) {
           m.bkey[blk] = key;
           coarse_set(m, bx, by, bz);
@@ -281,8 +281,8 @@ __device__ __forceinline__ bool in_box(const float4 p, const float* b) {  // ikd
 __device__ __forceinline__ void release_block(const MapDev& m, int blk, uint64_t key) {
   uint32_t s = hash_key(key) & m.hash_mask;
   for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
-    uint64_t k = *((volatile uint64_t*)&m.keys[s]);
-    if (k == key) { m.keys[s] = KEY_TOMB; break; }
+    uint64_t k = *((volatile uint64_t*)&m.hent[s].key);
+    if (k == key) { m.hent[s].key = KEY_TOMB; break; }
     if (k == KEY_EMPTY) break;
     s = (s + 1) & m.hash_mask;
   }
@@ -457,8 +457,8 @@ __global__ void k_rehash_insert(MapDev m, int nblk) {
     if (key == KEY_EMPTY) continue;
     uint32_t s = hash_key(key) & m.hash_mask;
     for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
-      uint64_t old = atomicCAS((unsigned long long*)&m.keys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-      if (old == KEY_EMPTY) { m.vals[s] = (uint32_t)b; break; }
+      uint64_t old = atomicCAS((unsigned long long*)&m.hent[s].key, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+      if (old == KEY_EMPTY) { m.hent[s].val = (uint32_t)b; break; }
       s = (s + 1) & m.hash_mask;
     }
     int bx, by, bz;

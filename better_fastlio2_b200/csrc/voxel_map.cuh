@@ -7,7 +7,7 @@
 //   coarse c = b >> 3   (8x8x8 blocks; 512-bit block-occupancy bitmap) — only used to bound far searches.
 //
 // Storage in HBM
-//   keys[C]/vals[C]   open-addressing hash  block key -> block index   (C = 2^k >= 2*B, 8+4 B per entry)
+//   hent[C]           open-addressing hash  block key -> block index   (C = 2^k >= 2*B, one 16-B entry per slot)
 //   bmask[B]          64-bit voxel occupancy of a block
 //   slots[B*64]       float4 head point of each voxel: x,y,z and w = int index of an overflow node (-1: none).
 //                     INVARIANT: w == -1 whenever the voxel has no overflow chain (also while the voxel is empty).
@@ -45,9 +45,15 @@ enum Counter : int {
 };
 enum DevError : int { ERR_BLOCKS_FULL = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4, ERR_COARSE_FULL = 8, ERR_RANGE = 16 };
 
+// one hash entry: key and block index side by side so that a lookup is ONE 16-byte load
+struct __align__(16) HEntry {
+  uint64_t key;
+  uint32_t val;
+  uint32_t pad;
+};
+
 struct MapDev {
-  uint64_t* keys;
-  uint32_t* vals;
+  HEntry* hent;
   uint64_t* bmask;
   float4* slots;
   float4* ovf;
@@ -73,13 +79,14 @@ __host__ __device__ __forceinline__ void unpack_key(uint64_t k, int& x, int& y, 
   y = (int)((k >> 21) & 0x1FFFFF) - COORD_BIAS;
   z = (int)(k & 0x1FFFFF) - COORD_BIAS;
 }
+// spatial hash of the three 21-bit biased coordinates (32-bit multiplies only: the lookup is on the k-NN hot path)
 __host__ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return (uint32_t)k;
+  const uint32_t x = (uint32_t)(k >> 42), y = (uint32_t)(k >> 21) & 0x1FFFFFu, z = (uint32_t)k & 0x1FFFFFu;
+  uint32_t h = (x * 73856093u) ^ (y * 19349663u) ^ (z * 83492791u);
+  h ^= h >> 15;
+  h *= 0x9E3779B1u;
+  h ^= h >> 13;
+  return h;
 }
 
 // voxel index of a coordinate: the reference's floor(x/downsample_size) in float (ikd_Tree.cpp:424).
@@ -89,8 +96,9 @@ __device__ __forceinline__ int voxel_of(float x, float ds) { return (int)floorf(
 __device__ __forceinline__ int find_block(const MapDev& m, uint64_t key) {
   uint32_t s = hash_key(key) & m.hash_mask;
   for (int probe = 0; probe <= (int)m.hash_mask; ++probe) {
-    uint64_t k = __ldg(&m.keys[s]);
-    if (k == key) return (int)__ldg(&m.vals[s]);
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(&m.hent[s]));
+    const uint64_t k = ((uint64_t)e.y << 32) | e.x;
+    if (k == key) return (int)e.z;
     if (k == KEY_EMPTY) return -1;
     s = (s + 1) & m.hash_mask;
   }

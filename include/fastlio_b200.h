@@ -99,6 +99,19 @@ typedef struct flb_map_stats {
 } flb_map_stats;
 int flb_map_get_stats(flb_map* m, flb_map_stats* out);
 
+/* Optional per-kernel-class timing with CUDA events on the map's stream (used by bench.py for the roofline figure;
+ * no reference counterpart — the reference's own timers are omp_get_wtime marks, laserMapping.cpp:2253-2402). */
+enum { FLB_K_TRANSFORM = 0, FLB_K_KNN, FLB_K_RESIDUAL, FLB_K_REDUCE, FLB_K_CLASSIFY, FLB_K_INSERT, FLB_K_DELETE, FLB_K_COUNT = 8 };
+typedef struct flb_profile {
+  double ms[FLB_K_COUNT];      /* accumulated device time per class */
+  int launches[FLB_K_COUNT];   /* kernels launched per class */
+  int regions[FLB_K_COUNT];    /* timed regions per class (e.g. one per k-NN pass) */
+  long long knn_phase[4];      /* queries resolved by search phase A (5^3 voxel stencil) / B0 (3^3 blocks) /
+                                  B (3^3 coarse cells) / C (exhaustive coarse scan) */
+} flb_profile;
+int flb_map_profile_enable(flb_map* m, int on);
+int flb_map_profile_read(flb_map* m, flb_profile* out, int reset);
+
 /* ------------------------------------------------------------------------------------------------ session (per scan) */
 typedef struct flb_session_config {
   int max_scan_points;      /* capacity N of feats_down_body (the reference caps at 100000, laserMapping.cpp:52) */
