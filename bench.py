@@ -35,14 +35,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+TINY = False  # --tiny: test-only shrink of the workload (NOT a bench configuration; used by tests/test_bench_dist.py)
+
+
 def make_workload(seed, n_scans, need_map=True):
     """Seeded cfg2 workload: world, map pre-fill (~5M pts), n_scans HDL-64 scans + priors along a 10 m/s trajectory."""
     from better_fastlio2_b200 import synth
     rng = np.random.default_rng(seed)
-    world = synth.city_world(half_extent=400.0, seed=seed)
-    dirs = synth.lidar_dirs("hdl64")
+    world = synth.city_world(half_extent=60.0 if TINY else 400.0, seed=seed)
+    dirs = synth.lidar_dirs("vlp16" if TINY else "hdl64")
     centre = (0.5 * n_scans, 0.0, 0.0)
-    mp = synth.sample_surface_map(world, centre, MAP_HALF, DS, rng) if need_map else None
+    mp = synth.sample_surface_map(world, centre, 20.0 if TINY else MAP_HALF, DS, rng) if need_map else None
     scans, priors, truths = [], [], []
     for k in range(n_scans):
         st = synth.trajectory_state(k, speed=10.0)
@@ -123,6 +126,21 @@ def cpu_step_runner(work, threads):
         return s
 
     return mp, step, build_s
+
+
+def dist_max(values, device=None, group_ready=None):
+    """Max over ranks of a list of floats (NCCL on GPUs, gloo on CPU); identity when not distributed."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=device if device is not None else "cpu")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def aggregate_scans_per_s(world_size, steps, ms_max):
+    """Whole-job throughput: every rank processed `steps` scans of its own session (weak scaling) in ms_max."""
+    return world_size * steps / (ms_max * 1e-3)
 
 
 def run_reference(args):
@@ -239,10 +257,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
-    tms = torch.tensor([ms, e2e_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(tms[0]), float(tms[1])
+    ms_max, e2e_ms_max = dist_max([ms, e2e_s * 1e3], device=f"cuda:{local}")
     stats = tree.stats()
     if rank == 0:
         peaks = {}
@@ -261,7 +276,7 @@ def run_b200(args):
                 traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        value = world_size * K / (ms_max * 1e-3)
+        value = aggregate_scans_per_s(world_size, K, ms_max)
         out = {
             "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world_size, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -273,7 +288,7 @@ def run_b200(args):
                                     "+ a new scan every step",
                        "pose_err_vs_truth_max_m": perr},
             "gpu_launches": launches,
-            "e2e": {"value": world_size * K / (e2e_ms_max * 1e-3), "unit": "scans/s",
+            "e2e": {"value": aggregate_scans_per_s(world_size, K, e2e_ms_max), "unit": "scans/s",
                     "h2d_bytes_per_step": int(16 * n_mean), "d2h_bytes_per_step": int(passes / K * 93 * 8 + 2 * 128 + 8)},
             "roofline": {"bound": "hbm", "kernel": "k_knn<5> (5-NN search pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -318,7 +333,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="test-only: shrink the workload (not a bench configuration)")
     args = ap.parse_args()
+    global TINY
+    TINY = args.tiny
     if args.warmup < 3 and args.impl == "b200":
         log("note: timing rules ask for >= 3 warm-up steps")
     if args.impl == "reference":

@@ -1,0 +1,77 @@
+"""Golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py in the build container from the
+reference ikd-Tree compiled unmodified + the restated update).  CPU: the oracle reproduces them wherever it runs.
+GPU: the CUDA path through the C ABI reproduces them on the B200 box (where /root/reference does not exist)."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import sort_rows
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+@pytest.mark.parametrize("backend", ["port", "reference"])
+def test_oracle_reproduces_golden(oracle, path, backend):
+    g = np.load(path)
+    if backend == "reference" and not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    m = oracle.RefIkdTree(ds=0.2) if backend == "reference" else oracle.PortMap(ds=0.2)
+    m.Build(g["map"])
+    ext = bool(g["ext"])
+    w0 = oracle.transform(g["prior"], g["body"])
+    x0, d0, c0 = m.Nearest_Search(w0, 5)
+    assert np.array_equal(c0, g["nn_cnt"]) and np.array_equal(d0, g["nn_d2"])
+    sel = np.ones(len(w0), np.uint8)
+    M0, hx0, h0, nv0, tot0 = oracle.residual_pass(g["prior"], g["body"], w0, x0, d0, c0, True, sel, ext)
+    assert M0 == int(g["M0"]) and np.array_equal(sel, g["sel0"])
+    assert np.allclose(hx0.T @ hx0, g["HTH0"], rtol=1e-12, atol=1e-12)
+    st, P, sc, stats, trace = oracle.esikf_update(g["prior"], g["P"], g["body"], m, max_iter=3, extrinsic_est_en=ext,
+                                                  want_trace=True)
+    assert np.array_equal(stats, g["stats"])
+    assert np.allclose(st, g["post"], rtol=0, atol=1e-11)
+    assert np.allclose(P, g["P_post"], rtol=1e-8, atol=1e-14)
+    wpost, cls = oracle.map_incremental_classify(st, g["body"], sc.nbr, sc.nbr_cnt, True, 0.2)
+    assert np.array_equal(cls, g["cls"])
+    m.Add_Points(wpost[cls == 1], True)
+    m.Add_Points(wpost[cls == 2], False)
+    final = sort_rows(m.flatten())
+    assert len(final) == int(g["final_count"]) and _digest(final) == str(g["final_sha256"])
+    # the posterior is a real improvement on the prior
+    assert np.linalg.norm(st[:3] - g["truth"][:3]) < 0.5 * np.linalg.norm(g["prior"][:3] - g["truth"][:3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_cuda_path_reproduces_golden(path):
+    from better_fastlio2_b200 import capi
+    g = np.load(path)
+    ext = bool(g["ext"])
+    t = capi.KDTree(voxel_size=0.2, max_points=1 << 19, max_blocks=1 << 16)
+    t.Build(g["map"])
+    ses = capi.Session(t, max_scan_points=len(g["body"]), extrinsic_est_en=ext, max_iterations=3)
+    ses.scan_upload(g["body"])
+    r = ses.h_share_model(g["prior"], converge=True)
+    nb = ses.neighbors()
+    assert np.array_equal(nb["cnt"], g["nn_cnt"]) and np.array_equal(nb["d2"], g["nn_d2"])   # bit-exact distances
+    assert r["effct_feat_num"] == int(g["M0"]) and np.array_equal(nb["sel"], g["sel0"])
+    assert np.allclose(r["HTH"], g["HTH0"], rtol=1e-9, atol=1e-9 * np.abs(g["HTH0"]).max())
+    assert np.allclose(r["HTh"], g["HTh0"], rtol=1e-9, atol=1e-9 * np.abs(g["HTh0"]).max())
+    ses.scan_upload(g["body"])
+    st, P, us = ses.update_iterated_dyn_share_modified(g["prior"], g["P"])
+    assert [us["passes"], us["search_passes"], us["effct_feat_num"], us["converged_count"]] == list(g["stats"])
+    assert np.abs(st - g["post"]).max() < 1e-8        # north_star tolerance is 1e-4 m / rad
+    assert np.allclose(P, g["P_post"], rtol=1e-6, atol=1e-12)
+    na, nn = ses.map_incremental(st, True)
+    assert na == int((g["cls"] == 1).sum()) and nn == int((g["cls"] == 2).sum())
+    final = sort_rows(t.flatten())
+    assert len(final) == int(g["final_count"]) and _digest(final) == str(g["final_sha256"])
+    ses.close()
+    t.close()
