@@ -26,7 +26,7 @@ dist.init_process_group("gloo")
 r = dist.get_rank()
 ms, e2e = bench.dist_max([100.0 + 50.0 * r, 7.0 - r])
 val = bench.aggregate_scans_per_s(dist.get_world_size(), 20, ms)
-os.write(1, ("RESULT %d %r %r %r\n" % (r, ms, e2e, val)).encode())
+os.write(1, ("RESULT {} {!r} {!r} {!r}\n".format(r, ms, e2e, val)).encode())
 dist.barrier()
 dist.destroy_process_group()
 '''
