@@ -1,0 +1,90 @@
+// Compiles the C++ facades the way src/laserMapping.cpp uses the reference headers (KD_TREE<PointType> global,
+// h_share_model callback with state_ikfom / dyn_share_datastruct look-alikes) and, when a GPU is present, runs them.
+// Built by tests/test_facade_cpp.py with:  g++ -Ioracle/shim -Iinclude tests/cpp/facade_smoke.cpp -Lbetter_fastlio2_b200 -lfastlio_b200
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include <fastlio_b200/ikd_tree_facade.hpp>
+#include <fastlio_b200/lio_gpu_frontend.hpp>
+
+typedef pcl::PointXYZINormal PointType;                       // common_lib.h:161
+typedef std::vector<PointType, Eigen::aligned_allocator<PointType>> PointVector;  // common_lib.h:163
+
+// minimal stand-ins with the member names of use-ikfom.hpp:21-30 / esekfom.hpp:79-89 (Eigen is absent in this image)
+struct Vec3 { double v[3]; double operator[](int i) const { return v[i]; } };
+struct Quat { double c[4]; const double* coeffs() const { return c; } };
+struct state_ikfom { Vec3 pos; Quat rot; Quat offset_R_L_I; Vec3 offset_T_L_I, vel, bg, ba, grav; };
+struct MatX { std::vector<double> a; int r = 0, c = 0; void resize(int R, int C) { r = R; c = C; a.assign((size_t)R * C, 0.0); } double* data() { return a.data(); } int rows() const { return r; } };
+struct VecX { std::vector<double> a; void resize(int n) { a.assign(n, 0.0); } double* data() { return a.data(); } };
+struct dyn_share_datastruct { bool valid = true, converge = true; MatX h_x; VecX h; };
+
+KD_TREE<PointType> ikdtree;  // laserMapping.cpp:116
+flb::LioGpu gpu;
+void h_share_model(state_ikfom& s, dyn_share_datastruct& d) { gpu.h_share_model(s, d); }
+
+int main() {
+  if (flb_device_count() <= 0) { std::printf("NO_GPU compile-only ok\n"); return 0; }
+  std::mt19937 rng(5);
+  std::uniform_real_distribution<float> U(-10.f, 10.f);
+  std::normal_distribution<float> N(0.f, 0.01f);
+  PointVector cloud;
+  for (int i = 0; i < 60000; ++i) { PointType p{}; p.x = U(rng); p.y = U(rng); p.z = N(rng); cloud.push_back(p); }           // ground
+  for (int i = 0; i < 30000; ++i) { PointType p{}; p.x = 6.f + N(rng); p.y = U(rng); p.z = 0.3f * (U(rng) + 10.f); cloud.push_back(p); }  // wall
+  ikdtree.set_capacity(1 << 20, 1 << 16);
+  if (ikdtree.Root_Node != nullptr) return 2;
+  ikdtree.set_downsample_param(0.2f);
+  ikdtree.Build(cloud);
+  if (ikdtree.Root_Node == nullptr || ikdtree.validnum() != (int)cloud.size() || ikdtree.size() != (int)cloud.size()) return 3;
+  PointVector near; std::vector<float> d2;
+  PointType q{}; q.x = 1.f; q.y = 2.f; q.z = 0.05f;
+  ikdtree.Nearest_Search(q, 5, near, d2);
+  if (near.size() != 5 || !(d2[0] <= d2[4]) || d2[4] > 0.2f) return 4;
+  // brute-force check of the nearest distance
+  float best = 1e30f;
+  for (auto& p : cloud) { float d = (p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y) + (p.z - q.z) * (p.z - q.z); if (d < best) best = d; }
+  if (best != d2[0]) return 5;
+  PointVector add = cloud; add.resize(2000);
+  for (auto& p : add) p.z += 0.05f;
+  ikdtree.Add_Points(add, true);
+  std::vector<BoxPointType> boxes(1);
+  boxes[0] = BoxPointType{{-10.f, -10.f, -1.f}, {0.f, 10.f, 10.f}};
+  const int before = ikdtree.validnum();
+  const int nd = ikdtree.Delete_Point_Boxes(boxes);
+  if (nd <= 0 || ikdtree.validnum() != before - nd) return 6;
+  PointVector().swap(ikdtree.PCL_Storage);
+  ikdtree.flatten(ikdtree.Root_Node, ikdtree.PCL_Storage, NOT_RECORD);  // laserMapping.cpp:2363-2364
+  if ((int)ikdtree.PCL_Storage.size() != ikdtree.validnum()) return 7;
+
+  // measurement callback on a scan = a noisy subsample of the remaining cloud seen from the origin
+  if (!gpu.attach(ikdtree.handle(), false, 3, 0.2)) return 8;
+  PointVector body;
+  for (size_t i = 0; i < ikdtree.PCL_Storage.size(); i += 7) body.push_back(ikdtree.PCL_Storage[i]);
+  gpu.begin_scan(&body[0].x, (int)body.size(), sizeof(PointType));
+  state_ikfom s{};
+  s.rot.c[3] = 1.0; s.offset_R_L_I.c[3] = 1.0; s.grav.v[2] = -9.809;
+  s.pos.v[0] = 0.02; s.pos.v[2] = -0.01;  // small prior error
+  dyn_share_datastruct d;
+  h_share_model(s, d);
+  if (!d.valid || d.h_x.rows() != gpu.effct_feat_num || gpu.effct_feat_num < 1000) return 9;
+  const int M = d.h_x.rows();
+  gpu.set_row_mode(flb::LioGpu::COMPRESSED_ROWS);
+  dyn_share_datastruct d2s; d2s.converge = false;
+  h_share_model(s, d2s);
+  if (!d2s.valid || d2s.h_x.rows() != 24) return 10;
+  // compressed rows reproduce H^T H and H^T h of the exact rows
+  double maxerr = 0, scale = 0;
+  for (int a = 0; a < 12; ++a)
+    for (int b = 0; b < 12; ++b) {
+      double e = 0, c = 0;
+      for (int r = 0; r < M; ++r) e += d.h_x.a[(size_t)a * M + r] * d.h_x.a[(size_t)b * M + r];
+      for (int r = 0; r < 24; ++r) c += d2s.h_x.a[(size_t)a * 24 + r] * d2s.h_x.a[(size_t)b * 24 + r];
+      maxerr = std::fmax(maxerr, std::fabs(e - c)); scale = std::fmax(scale, std::fabs(e));
+    }
+  if (maxerr > 1e-9 * scale) { std::printf("HTH mismatch %g / %g\n", maxerr, scale); return 11; }
+  const int added = gpu.map_incremental(s, true);
+  std::printf("FACADE_OK M=%d deleted=%d map=%d added=%d\n", M, nd, ikdtree.validnum(), added);
+  return 0;
+}
