@@ -73,7 +73,7 @@ EXPORTS = [
     "flb_map_get_stats", "flb_session_default_config", "flb_session_create", "flb_session_destroy", "flb_scan_upload",
     "flb_scan_set_device", "flb_pass", "flb_pass_rows", "flb_esikf_update", "flb_map_incremental",
     "flb_neighbors_download", "flb_fov_segment", "flb_scan_step", "flb_session_stream", "flb_session_sync",
-    "flb_map_profile_enable", "flb_map_profile_read",
+    "flb_map_profile_enable", "flb_map_profile_read", "flb_session_set_update_engine",
 ]
 
 
@@ -123,6 +123,7 @@ def lib():
         L.flb_session_stream.argtypes = [vp]
         L.flb_session_stream.restype = vp
         L.flb_session_sync.argtypes = [vp]
+        L.flb_session_set_update_engine.argtypes = [vp, C.c_int]
         L.flb_map_profile_enable.argtypes = [vp, C.c_int]
         L.flb_map_profile_read.argtypes = [vp, C.POINTER(Profile), C.c_int]
         _lib = L
@@ -363,6 +364,9 @@ class Session:
         _chk(lib().flb_scan_step(self.h, C.byref(fov) if fov is not None else None, C.c_void_p(ptr) if ptr else None,
                                  int(n), int(stride), _p(state26), _p(P), 1 if flg_EKF_inited else 0, C.byref(r)))
         return r
+
+    def set_update_engine(self, device_driven=True):
+        _chk(lib().flb_session_set_update_engine(self.h, 1 if device_driven else 0))
 
     def stream_ptr(self):
         return lib().flb_session_stream(self.h)

@@ -1,0 +1,436 @@
+// esikf_device.cuh — the iterated error-state Kalman update (esekfom.hpp:1620-1938) kept RESIDENT ON THE DEVICE so a
+// whole scan (<= max_iter+1 measurement passes + map insert) runs as one launch sequence without host round trips.
+// One thread block per step: all threads reduce the per-block normal-equation partials in a fixed order, then warp 0
+// does the 23-DOF algebra co-operatively on shared-memory matrices (two 23x23 Gauss-Jordan inverses with partial
+// pivoting, the SO3 / S2 projections of esekfom.hpp:1663-1703, boxplus, convergence bookkeeping :1824-1838 and the
+// final covariance :1841-1931).  Same mathematics as csrc/esikf_host.hpp (which remains the host-driven path and the
+// fallback for the under-determined M < 23 branch, esekfom.hpp:1720-1750).
+#pragma once
+#include "meas_kernels.cuh"
+
+namespace flb {
+
+namespace dev {
+
+__device__ __forceinline__ void qmul(const double* a, const double* b, double* r) {  // (x,y,z,w)
+  const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  const double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  r[0] = x; r[1] = y; r[2] = z; r[3] = w;
+}
+__device__ __forceinline__ void rotmat(const double* q, double* R) {
+  const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ __forceinline__ void hat(const double* v, double* H) {
+  H[0] = 0; H[1] = -v[2]; H[2] = v[1]; H[3] = v[2]; H[4] = 0; H[5] = -v[0]; H[6] = -v[1]; H[7] = v[0]; H[8] = 0;
+}
+__device__ __forceinline__ void mm3(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j]; C[3 * i + j] = s; }
+}
+__device__ __forceinline__ void cos_sinc_sqrt(double x2, double& c, double& s) {  // mtkmath.hpp:142-174
+  const double bound = 1.220703125e-4;  // sqrt(sqrt(eps))
+  if (x2 >= bound) { const double x = sqrt(x2); c = cos(x); s = sin(x) / x; return; }
+  const double inv[7] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
+  double cosi = 1., sinc = 1., term = -1 / 2. * x2;
+  for (int i = 0; i < 3; ++i) { cosi += term; term *= inv[2 * i]; sinc += term; term *= -inv[2 * i + 1] * x2; }
+  c = cosi; s = sinc;
+}
+__device__ __forceinline__ void exp_quat(const double* v, double scale, double* q) {  // mtkmath.hpp:249-256
+  const double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  double c, s;
+  cos_sinc_sqrt(scale * scale * n2, c, s);
+  const double m = s * scale;
+  q[0] = m * v[0]; q[1] = m * v[1]; q[2] = m * v[2]; q[3] = c;
+}
+__device__ __forceinline__ void log_quat(const double* q, double* r) {  // SOn.hpp:293-297
+  double nv = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  if (nv < 1e-11) nv = 1e-11;
+  const double s = 2.0 / nv * atan(nv / q[3]);
+  r[0] = s * q[0]; r[1] = s * q[1]; r[2] = s * q[2];
+}
+__device__ __forceinline__ void A_matrix_T(const double* v, double* J) {  // A_matrix(v)^T, mtkmath.hpp:235-247
+  const double sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  const double n = sqrt(sq);
+  double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (n >= 1e-11) {
+    double H[9], HH[9];
+    hat(v, H);
+    mm3(H, H, HH);
+    const double a = (1 - cos(n)) / sq, b = (1 - sin(n) / n) / sq;
+    for (int i = 0; i < 9; ++i) A[i] = A[i] + a * H[i] + b * HH[i];
+  }
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[3 * i + j] = A[3 * j + i];
+}
+__device__ __forceinline__ void s2_Bx(const double* vec, double* Bx) {  // S2.hpp:215-231, 3x2 row-major
+  const double len = 98090.0 / 10000.0;
+  if (vec[0] + len > 1e-11) {
+    Bx[0] = -vec[1]; Bx[1] = -vec[2];
+    Bx[2] = len - vec[1] * vec[1] / (len + vec[0]); Bx[3] = -vec[2] * vec[1] / (len + vec[0]);
+    Bx[4] = -vec[2] * vec[1] / (len + vec[0]); Bx[5] = len - vec[2] * vec[2] / (len + vec[0]);
+    for (int i = 0; i < 6; ++i) Bx[i] /= len;
+  } else {
+    for (int i = 0; i < 6; ++i) Bx[i] = 0;
+    Bx[3] = -1; Bx[4] = 1;
+  }
+}
+// J (2x2) = Nx_yy(xg) * Mx(xpg, delta)   (S2.hpp:259-280, esekfom.hpp:1693-1695)
+__device__ __forceinline__ void s2_jac(const double* xg, const double* xpg, const double* delta, double* J) {
+  const double len = 98090.0 / 10000.0;
+  double Bx[6], H[9], Nx[6];
+  s2_Bx(xg, Bx);
+  hat(xg, H);
+  const double sc = 1 / len / len;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += (sc * Bx[2 * k + i]) * H[3 * k + j]; Nx[3 * i + j] = s; }
+  double Bp[6], Hp[9], Mx[6];
+  s2_Bx(xpg, Bp);
+  hat(xpg, Hp);
+  const double dn = sqrt(delta[0] * delta[0] + delta[1] * delta[1]);
+  if (dn < 1e-11) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += (-Hp[3 * i + k]) * Bp[2 * k + j]; Mx[2 * i + j] = s; }
+  } else {
+    double Bu[3];
+    for (int i = 0; i < 3; ++i) Bu[i] = Bp[2 * i] * delta[0] + Bp[2 * i + 1] * delta[1];
+    double q[4], E[9], At[9], T1[9], T2[9];
+    exp_quat(Bu, 0.0, q);  // scalar(1/2) == 0 in the reference (S2.hpp:277)
+    rotmat(q, E);
+    A_matrix_T(Bu, At);
+    for (int i = 0; i < 9; ++i) E[i] = -E[i];
+    mm3(E, Hp, T1);
+    mm3(T1, At, T2);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += T2[3 * i + k] * Bp[2 * k + j]; Mx[2 * i + j] = s; }
+  }
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += Nx[3 * i + k] * Mx[2 * k + j]; J[2 * i + j] = s; }
+}
+__device__ __forceinline__ void state_boxplus(double* x, const double* d) {  // build_manifold.hpp:188-190
+  for (int i = 0; i < 3; ++i) x[i] += d[i];
+  double q[4];
+  exp_quat(d + 3, 0.5, q); qmul(x + 3, q, x + 3);
+  exp_quat(d + 6, 0.5, q); qmul(x + 7, q, x + 7);
+  for (int i = 0; i < 3; ++i) { x[11 + i] += d[9 + i]; x[14 + i] += d[12 + i]; x[17 + i] += d[15 + i]; x[20 + i] += d[18 + i]; }
+  double Bx[6], Bu[3], R[9], o[3];
+  s2_Bx(x + 23, Bx);
+  for (int i = 0; i < 3; ++i) Bu[i] = Bx[2 * i] * d[21] + Bx[2 * i + 1] * d[22];
+  exp_quat(Bu, 0.5, q);
+  rotmat(q, R);
+  for (int i = 0; i < 3; ++i) o[i] = R[3 * i] * x[23] + R[3 * i + 1] * x[24] + R[3 * i + 2] * x[25];
+  x[23] = o[0]; x[24] = o[1]; x[25] = o[2];
+}
+__device__ __forceinline__ void state_boxminus(const double* x, const double* o, double* r) {  // x [-] o
+  for (int i = 0; i < 3; ++i) r[i] = x[i] - o[i];
+  double qc[4], q[4];
+  qc[0] = -o[3]; qc[1] = -o[4]; qc[2] = -o[5]; qc[3] = o[6];
+  qmul(qc, x + 3, q); log_quat(q, r + 3);
+  qc[0] = -o[7]; qc[1] = -o[8]; qc[2] = -o[9]; qc[3] = o[10];
+  qmul(qc, x + 7, q); log_quat(q, r + 6);
+  for (int i = 0; i < 3; ++i) { r[9 + i] = x[11 + i] - o[11 + i]; r[12 + i] = x[14 + i] - o[14 + i]; r[15 + i] = x[17 + i] - o[17 + i]; r[18 + i] = x[20 + i] - o[20 + i]; }
+  // S2 boxminus (S2.hpp:144-167): this = x.grav, other = o.grav
+  const double* v = x + 23;
+  const double* ov = o + 23;
+  double H[9], t[3];
+  hat(v, H);
+  for (int i = 0; i < 3; ++i) t[i] = H[3 * i] * ov[0] + H[3 * i + 1] * ov[1] + H[3 * i + 2] * ov[2];
+  const double v_sin = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  const double v_cos = v[0] * ov[0] + v[1] * ov[1] + v[2] * ov[2];
+  const double theta = atan2(v_sin, v_cos);
+  if (v_sin < 1e-11) {
+    r[21] = fabs(theta) > 1e-11 ? 3.1415926 : 0.0;
+    r[22] = 0.0;
+  } else {
+    double Bx[6], Ho[9], u[3];
+    s2_Bx(ov, Bx);
+    hat(ov, Ho);
+    for (int i = 0; i < 3; ++i) u[i] = Ho[3 * i] * v[0] + Ho[3 * i + 1] * v[1] + Ho[3 * i + 2] * v[2];
+    const double f = theta / v_sin;
+    for (int i = 0; i < 2; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += (f * Bx[2 * k + i]) * u[k]; r[21 + i] = s; }
+  }
+}
+// ---- piecewise versions so that independent sub-manifolds are handled by different warps concurrently
+__device__ __forceinline__ void so3_boxminus(const double* xq, const double* oq, double* r) {  // log(o^-1 * x)
+  double qc[4] = {-oq[0], -oq[1], -oq[2], oq[3]}, q[4];
+  qmul(qc, xq, q);
+  log_quat(q, r);
+}
+__device__ __forceinline__ void so3_boxplus(double* xq, const double* d) {
+  double q[4];
+  exp_quat(d, 0.5, q);
+  qmul(xq, q, xq);
+}
+__device__ __forceinline__ void s2_boxminus(const double* v, const double* ov, double* r) {  // S2.hpp:144-167
+  double H[9], t[3];
+  hat(v, H);
+  for (int i = 0; i < 3; ++i) t[i] = H[3 * i] * ov[0] + H[3 * i + 1] * ov[1] + H[3 * i + 2] * ov[2];
+  const double v_sin = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  const double v_cos = v[0] * ov[0] + v[1] * ov[1] + v[2] * ov[2];
+  const double theta = atan2(v_sin, v_cos);
+  if (v_sin < 1e-11) {
+    r[0] = fabs(theta) > 1e-11 ? 3.1415926 : 0.0;
+    r[1] = 0.0;
+  } else {
+    double Bx[6], Ho[9], u[3];
+    s2_Bx(ov, Bx);
+    hat(ov, Ho);
+    for (int i = 0; i < 3; ++i) u[i] = Ho[3 * i] * v[0] + Ho[3 * i + 1] * v[1] + Ho[3 * i + 2] * v[2];
+    const double f = theta / v_sin;
+    for (int i = 0; i < 2; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += (f * Bx[2 * k + i]) * u[k]; r[i] = s; }
+  }
+}
+__device__ __forceinline__ void s2_boxplus(double* v, const double* d) {  // S2.hpp:136-142
+  double Bx[6], Bu[3], R[9], o[3], q[4];
+  s2_Bx(v, Bx);
+  for (int i = 0; i < 3; ++i) Bu[i] = Bx[2 * i] * d[0] + Bx[2 * i + 1] * d[1];
+  exp_quat(Bu, 0.5, q);
+  rotmat(q, R);
+  for (int i = 0; i < 3; ++i) o[i] = R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2];
+  v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+}
+__device__ __forceinline__ void pose_from_state(const double* x, PoseDev& p) {
+  for (int i = 0; i < 4; ++i) { p.rot[i] = x[3 + i]; p.offR[i] = x[7 + i]; }
+  for (int i = 0; i < 3; ++i) { p.pos[i] = x[i]; p.offT[i] = x[11 + i]; }
+}
+
+// ---- block-cooperative 23x23 helpers on shared memory (row-major, leading dimension NDOF); every thread of the
+// block calls them (they contain __syncthreads)
+constexpr int ESIKF_THREADS = 256;
+// rows [idx, idx+D) of Dst <- J * rows of Src
+template <int D>
+__device__ __forceinline__ void b_mul_rows(double* Dst, const double* Src, int idx, const double* J, int tid) {
+  double t[D];
+  if (tid < NDOF) {
+    for (int i = 0; i < D; ++i) { double s = 0; for (int k = 0; k < D; ++k) s += J[D * i + k] * Src[(idx + k) * NDOF + tid]; t[i] = s; }
+  }
+  __syncthreads();
+  if (tid < NDOF) for (int i = 0; i < D; ++i) Dst[(idx + i) * NDOF + tid] = t[i];
+  __syncthreads();
+}
+template <int D>
+__device__ __forceinline__ void b_mul_cols_T(double* M, int idx, const double* J, int tid) {
+  double t[D];
+  if (tid < NDOF) {
+    for (int j = 0; j < D; ++j) { double s = 0; for (int k = 0; k < D; ++k) s += M[tid * NDOF + idx + k] * J[D * j + k]; t[j] = s; }
+  }
+  __syncthreads();
+  if (tid < NDOF) for (int j = 0; j < D; ++j) M[tid * NDOF + idx + j] = t[j];
+  __syncthreads();
+}
+// Inverse of A (23x23) by Gauss-Jordan with partial pivoting on aug = [A | I] (23 x 46), ping-pong buffered so that one
+// pivot step = ONE barrier: every warp finds the pivot row redundantly (shuffles, first maximum wins), then each
+// thread writes new[r][j] from old values only:  row c <- old[piv]/pivot ;  other rows <- old[src] - old[src][c]*row c
+// (src = c for r == piv: the row swap).  aug must hold 2 * 23 * 46 doubles.  Result -> Ainv.
+__device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double* aug, int tid) {
+  constexpr int W = 2 * NDOF;
+  constexpr int SZ = NDOF * W;
+  const int lane = tid & 31;
+  for (int e = tid; e < SZ; e += ESIKF_THREADS) {
+    const int r = e / W, c = e - r * W;
+    aug[e] = c < NDOF ? A[r * NDOF + c] : ((c - NDOF) == r ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  double* cur = aug;
+  double* nxt = aug + SZ;
+  for (int c = 0; c < NDOF; ++c) {
+    double best = -1.0;
+    int piv = c;
+    if (c + lane < NDOF) { best = fabs(cur[(c + lane) * W + c]); piv = c + lane; }
+    for (int o = 16; o; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int op = __shfl_xor_sync(FULL, piv, o);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    const double d = 1.0 / cur[piv * W + c];
+    for (int e = tid; e < SZ; e += ESIKF_THREADS) {
+      const int r = e / W, j = e - r * W;
+      const double pr = cur[piv * W + j] * d;
+      if (r == c) nxt[e] = pr;
+      else {
+        const int src = (r == piv) ? c : r;
+        nxt[e] = cur[src * W + j] - cur[src * W + c] * pr;
+      }
+    }
+    __syncthreads();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) { const int r = e / NDOF; Ainv[e] = cur[r * W + NDOF + (e - r * NDOF)]; }
+  __syncthreads();
+}
+
+}  // namespace dev
+
+// Load the propagated state / covariance for a new scan.
+__global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ x0, const double* __restrict__ P0, int n) {
+  for (int i = threadIdx.x; i < NDOF * NDOF; i += blockDim.x) { c->Pp[i] = P0[i]; c->P[i] = P0[i]; }
+  if (threadIdx.x < 26) { c->x[threadIdx.x] = x0[threadIdx.x]; c->xp[threadIdx.x] = x0[threadIdx.x]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c->it = -1; c->t = 0; c->converge = 1; c->finished = 0; c->need_host = 0; c->passes = 0; c->searches = 0;
+    c->lastM = 0; c->last_res = 0.0; c->n = n;
+    dev::pose_from_state(c->x, c->pose);
+  }
+}
+
+// One loop iteration of update_iterated_dyn_share_modified after the measurement pass wrote its block partials.
+__global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_step(EsikfCtl* c, const double* __restrict__ partial, int nblocks) {
+  using namespace dev;
+  __shared__ double acc[NACC];
+  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[NDOF * NDOF], aug[2 * NDOF * 2 * NDOF];
+  __shared__ double Kx[NDOF * 12], HTH[144], HTh[12], Kh[NDOF];
+  __shared__ double dx[NDOF], dxn[NDOF], dx_[NDOF], J3a[9], J3b[9], J2[4], xs[26], xps[26];
+  __shared__ int s_go, s_fin, s_conv, s_tt;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_go = (!c->finished && c->it < c->max_iter && c->n > 0) ? 1 : 0;
+  __syncthreads();
+  if (!s_go) {
+    // loop already ended; an empty scan still consumes its passes (every pass invalid)
+    if (tid == 0 && !c->finished && c->it < c->max_iter && c->n <= 0) { c->it++; c->passes++; }
+    return;
+  }
+  // ---- fixed-order reduction of the per-block partials (role of K2): 2 threads per entry, halves combined in order
+  {
+    const int e = tid >> 1, h = tid & 1;
+    double s = 0.0;
+    if (e < NACC) {
+      const int half = (nblocks + 1) >> 1;
+      const int b0 = h ? half : 0, b1 = h ? nblocks : half;
+      for (int b = b0; b < b1; ++b) s += partial[(size_t)b * NACC + e];
+    }
+    const double o = __shfl_xor_sync(FULL, s, 1);
+    if (e < NACC && h == 0) acc[e] = s + o;
+  }
+  __syncthreads();
+  const int M = (int)(acc[92] + 0.5);
+  if (tid == 0) { c->passes++; if (c->converge) c->searches++; }
+  if (M < 1) { if (tid == 0) c->it++; return; }                                   // valid = false -> continue (:1641-1644)
+  if (M < NDOF) { if (tid == 0) { c->need_host = 1; c->finished = 1; } return; }  // under-determined branch: host path
+  const double R = c->R;
+  const int it = c->it, max_iter = c->max_iter;
+  if (tid < 144) {
+    const int i = tid / 12, j = tid - i * 12;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    HTH[tid] = acc[a * 13 - a * (a - 1) / 2 + (b - a)];
+  }
+  if (tid >= 160 && tid < 172) { const int l = tid - 160; HTh[l] = acc[l * 13 - l * (l - 1) / 2 + (12 - l)]; }
+  if (tid >= 192 && tid < 218) { xs[tid - 192] = c->x[tid - 192]; xps[tid - 192] = c->xp[tid - 192]; }
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) P[e] = c->Pp[e];
+  __syncthreads();
+  // x_ [-] x_propagated (:1655) and the projection Jacobians, one sub-manifold per warp
+  if (tid == 0) {
+    c->lastM = M; c->last_res = acc[91];
+    so3_boxminus(xs + 3, xps + 3, dx + 3);
+    A_matrix_T(dx + 3, J3a);
+  } else if (tid == 32) {
+    so3_boxminus(xs + 7, xps + 7, dx + 6);
+    A_matrix_T(dx + 6, J3b);
+  } else if (tid == 64) {
+    s2_boxminus(xs + 23, xps + 23, dx + 21);
+    s2_jac(xs + 23, xps + 23, dx + 21, J2);
+  } else if (tid == 96) {
+    for (int i = 0; i < 3; ++i) {
+      dx[i] = xs[i] - xps[i]; dx[9 + i] = xs[11 + i] - xps[11 + i]; dx[12 + i] = xs[14 + i] - xps[14 + i];
+      dx[15 + i] = xs[17 + i] - xps[17 + i]; dx[18 + i] = xs[20 + i] - xps[20 + i];
+    }
+  }
+  __syncthreads();
+  if (tid < NDOF) {                                     // dx_new with the SO3 / S2 blocks projected (:1671, :1696)
+    double v = dx[tid];
+    if (tid >= 3 && tid < 6) { const int i = tid - 3; v = J3a[3 * i] * dx[3] + J3a[3 * i + 1] * dx[4] + J3a[3 * i + 2] * dx[5]; }
+    else if (tid >= 6 && tid < 9) { const int i = tid - 6; v = J3b[3 * i] * dx[6] + J3b[3 * i + 1] * dx[7] + J3b[3 * i + 2] * dx[8]; }
+    else if (tid >= 21) { const int i = tid - 21; v = J2[2 * i] * dx[21] + J2[2 * i + 1] * dx[22]; }
+    dxn[tid] = v;
+  }
+  __syncthreads();
+  b_mul_rows<3>(P, P, 3, J3a, tid);                     // SO3 blocks :1665-1681
+  b_mul_cols_T<3>(P, 3, J3a, tid);
+  b_mul_rows<3>(P, P, 6, J3b, tid);
+  b_mul_cols_T<3>(P, 6, J3b, tid);
+  b_mul_rows<2>(P, P, 21, J2, tid);                     // S2 block :1683-1703
+  b_mul_cols_T<2>(P, 21, J2, tid);
+  // information form :1788-1815
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) L[e] = P[e] / R;
+  __syncthreads();
+  b_inverse(L, T, aug, tid);                            // (P/R)^-1
+  if (tid < 144) T[(tid / 12) * NDOF + (tid % 12)] += HTH[tid];
+  __syncthreads();
+  b_inverse(T, L, aug, tid);                            // P_inv -> L
+  if (tid < NDOF) { double s = 0; for (int k = 0; k < 12; ++k) s += L[tid * NDOF + k] * HTh[k]; Kh[tid] = s; }
+  for (int e = tid; e < NDOF * 12; e += ESIKF_THREADS) {
+    const int i = e / 12, b = e - i * 12;
+    double q = 0;
+    for (int k = 0; k < 12; ++k) q += L[i * NDOF + k] * HTH[k * 12 + b];
+    Kx[e] = q;
+  }
+  __syncthreads();
+  if (tid < NDOF) {                                     // :1821 dx_ = K_h + (K_x - I) dx_new
+    double s = 0;
+    for (int j = 0; j < NDOF; ++j) s += ((j < 12 ? Kx[tid * 12 + j] : 0.0) - (tid == j ? 1.0 : 0.0)) * dxn[j];
+    dx_[tid] = Kh[tid] + s;
+  }
+  __syncthreads();
+  // x_ [+] dx_ (:1823), convergence test (:1824-1838) and the Jacobians of the final covariance, per sub-manifold
+  if (tid == 0) {
+    so3_boxplus(xs + 3, dx_ + 3);
+    A_matrix_T(dx_ + 3, J3a);
+  } else if (tid == 32) {
+    so3_boxplus(xs + 7, dx_ + 6);
+    A_matrix_T(dx_ + 6, J3b);
+  } else if (tid == 64) {
+    s2_boxplus(xs + 23, dx_ + 21);
+    s2_jac(xs + 23, xps + 23, dx_ + 21, J2);
+  } else if (tid == 96) {
+    for (int i = 0; i < 3; ++i) { xs[i] += dx_[i]; xs[11 + i] += dx_[9 + i]; xs[14 + i] += dx_[12 + i]; xs[17 + i] += dx_[15 + i]; xs[20 + i] += dx_[18 + i]; }
+  } else if (tid == 128) {
+    int conv = 1, tt = c->t;
+    for (int i = 0; i < NDOF; ++i) if (fabs(dx_[i]) > c->limit[i]) { conv = 0; break; }
+    if (conv) ++tt;
+    if (!tt && it == max_iter - 2) conv = 1;            // :1835-1838
+    s_conv = conv; s_tt = tt;
+    s_fin = (tt > 1 || it == max_iter - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  const int fin = s_fin;
+  if (fin) {                                            // :1841-1931
+    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) L[e] = P[e];
+    __syncthreads();
+    for (int b = 0; b < 2; ++b) {
+      const int idx = b == 0 ? 3 : 6;
+      const double* J3 = b == 0 ? J3a : J3b;
+      b_mul_rows<3>(L, P, idx, J3, tid);
+      double tv[3];
+      if (tid < 12) for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += J3[3 * i + k] * Kx[(idx + k) * 12 + tid]; tv[i] = s; }
+      __syncthreads();
+      if (tid < 12) for (int i = 0; i < 3; ++i) Kx[(idx + i) * 12 + tid] = tv[i];
+      __syncthreads();
+      b_mul_cols_T<3>(L, idx, J3, tid);
+      b_mul_cols_T<3>(P, idx, J3, tid);
+    }
+    b_mul_rows<2>(L, P, 21, J2, tid);
+    double a0 = 0, a1 = 0;
+    if (tid < 12) { a0 = J2[0] * Kx[21 * 12 + tid] + J2[1] * Kx[22 * 12 + tid]; a1 = J2[2] * Kx[21 * 12 + tid] + J2[3] * Kx[22 * 12 + tid]; }
+    __syncthreads();
+    if (tid < 12) { Kx[21 * 12 + tid] = a0; Kx[22 * 12 + tid] = a1; }
+    __syncthreads();
+    b_mul_cols_T<2>(L, 21, J2, tid);
+    b_mul_cols_T<2>(P, 21, J2, tid);
+    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) {      // P_ = L_ - K_x[:, :12] P_[:12, :]
+      const int i = e / NDOF, j = e - i * NDOF;
+      double s = 0;
+      for (int k = 0; k < 12; ++k) s += Kx[i * 12 + k] * P[k * NDOF + j];
+      c->P[e] = L[e] - s;
+    }
+  } else {
+    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) c->P[e] = P[e];  // P_ as last assigned (projected P_propagated)
+  }
+  if (tid < 26) c->x[tid] = xs[tid];
+  if (tid == 0) {
+    c->converge = s_conv; c->t = s_tt; c->finished = fin; c->it = it + 1;
+    pose_from_state(xs, c->pose);
+  }
+}
+
+}  // namespace flb

@@ -5,6 +5,7 @@
 #include "map_kernels.cuh"
 #include "knn_kernels.cuh"
 #include "meas_kernels.cuh"
+#include "esikf_device.cuh"
 #include "esikf_host.hpp"
 
 #include <cub/device/device_scan.cuh>
@@ -267,25 +268,25 @@ static int maybe_rehash(flb_map* m);
 
 // Insert device points. mode 0: verbatim (Build / Add_Points(false)); 1: downsample (Add_Points(true));
 // 2: classified (map_incremental: cls 1 -> downsample, cls 2 -> verbatim). Asynchronous on m->stream.
-static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode) {
+static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode, const int* skip = nullptr) {
   if (n <= 0) return 0;
   const int g = grid_for(n, 256, m->sm_count * 8);
   cudaStream_t st = m->stream;
   const unsigned char* c = (mode == 2) ? cls : nullptr;
   ProfScope ps(m, FLB_K_INSERT);
-  k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n);
+  k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n, skip);
   m->launches++;
   if (mode == 1 || mode == 2) {
     if (ensure_scratch(m, n)) return 1;
     const uint32_t sc = next_pow2((uint64_t)std::max(n, 512) * 2);
     CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
     CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
-    k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1);
-    k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1);
+    k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip);
+    k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip);
     m->launches += 2;
   }
   if (mode == 0 || mode == 2) {
-    k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n);
+    k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip);
     m->launches++;
   }
   CU(cudaGetLastError());
@@ -446,6 +447,7 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
   a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt;
   a.max_d2 = (max_dist > 0.f && max_dist < 1e18f) ? max_dist * max_dist : INFINITY;
   a.phase_stats = nullptr;
+  a.ctl = nullptr; a.body = nullptr;
   int lrc = (K == 5) ? launch_knn<5>(m, a) : launch_knn<20>(m, a);
   cudaError_t le = lrc ? cudaErrorUnknown : cudaGetLastError();
   std::vector<float4> h((size_t)nq * K);
@@ -611,6 +613,12 @@ struct flb_session {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   unsigned char* raw = nullptr;
   size_t raw_cap = 0;
+  // device-driven update
+  EsikfCtl* ctl = nullptr;       // device
+  EsikfCtl* h_ctl = nullptr;     // pinned mirror
+  double* d_x0P0 = nullptr;      // device staging of the propagated state (26) + covariance (529)
+  double* h_x0P0 = nullptr;      // pinned
+  bool device_update = true;
 };
 
 extern "C" void flb_session_default_config(flb_session_config* c) {
@@ -648,6 +656,10 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   A((void**)&s->offs, sizeof(int) * N);
   A((void**)&s->selint, sizeof(int) * N);
   A((void**)&s->d_cnt2, sizeof(int) * 8);
+  A((void**)&s->ctl, sizeof(EsikfCtl));
+  A((void**)&s->d_x0P0, sizeof(double) * (26 + NDOF * NDOF));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ctl, sizeof(EsikfCtl));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_out, sizeof(double) * NACC);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_cnt2, sizeof(int) * 8);
   if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -660,6 +672,14 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
     s->cub_tmp_bytes = tb;
     A(&s->cub_tmp, tb ? tb : 16);
   }
+  if (e == cudaSuccess) {
+    memset(s->h_ctl, 0, sizeof(EsikfCtl));
+    for (int i = 0; i < NDOF; ++i) s->h_ctl->limit[i] = cfg->limit[i];
+    s->h_ctl->R = cfg->laser_point_cov;
+    s->h_ctl->max_iter = cfg->max_iterations;
+    s->h_ctl->finished = 1;
+    e = cudaMemcpy(s->ctl, s->h_ctl, sizeof(EsikfCtl), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) { flb_session_destroy(s); return set_err("flb_session_create: %s", cudaGetErrorString(e)); }
   *out = s;
   return 0;
@@ -670,10 +690,12 @@ extern "C" void flb_session_destroy(flb_session* s) {
   cudaSetDevice(s->map->cfg.device);
   cudaStreamSynchronize(s->map->stream);
   void* ptrs[] = {s->body, s->world, s->nbr, s->normvec, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
-                  s->cub_tmp, s->drows, s->d_cnt2, s->raw};
+                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->ctl, s->d_x0P0};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->h_out) cudaFreeHost(s->h_out);
   if (s->h_cnt2) cudaFreeHost(s->h_cnt2);
+  if (s->h_ctl) cudaFreeHost(s->h_ctl);
+  if (s->h_x0P0) cudaFreeHost(s->h_x0P0);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev2) cudaEventDestroy(s->ev2);
@@ -681,6 +703,11 @@ extern "C" void flb_session_destroy(flb_session* s) {
   delete s;
 }
 
+extern "C" int flb_session_set_update_engine(flb_session* s, int device_driven) {
+  if (!s) return set_err("null session");
+  s->device_update = device_driven != 0;
+  return 0;
+}
 extern "C" void* flb_session_stream(flb_session* s) { return s ? (void*)s->map->stream : nullptr; }
 extern "C" int flb_session_sync(flb_session* s) {
   if (!s) return set_err("null session");
@@ -742,6 +769,7 @@ static MeasArgs meas_args(flb_session* s, const PoseDev& pose, int search) {
   MeasArgs a;
   a.pose = pose; a.body = s->body; a.world = s->world; a.nbr = s->nbr; a.cnt = s->cnt; a.sel = s->sel;
   a.normvec = s->normvec; a.partial = s->partial; a.n = s->n; a.search = search;
+  a.ctl = nullptr; a.world_out = s->world;
   return a;
 }
 
@@ -762,6 +790,7 @@ static int enqueue_pass(flb_session* s, const double* state26, int search) {
     KnnArgs a;
     a.m = m->d; a.q = s->world; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
     a.phase_stats = m->prof_on ? m->d_phase : nullptr;
+    a.ctl = nullptr; a.body = nullptr;
     if (launch_knn<5>(m, a)) return 1;
   }
   const MeasArgs ma = meas_args(s, pose, search);
@@ -893,27 +922,86 @@ static int run_update(flb_session* s, double* state26, double* P, flb_update_sta
   return 0;
 }
 
+
+// Device-driven update: every pass of the iterated update is enqueued up front (k-NN pair, residual, ESIKF step);
+// kernels of passes that turn out not to be needed exit on the device-side loop flags. No host round trip inside.
+static int enqueue_update_device(flb_session* s, const double* state26, const double* P) {
+  flb_map* m = s->map;
+  cudaStream_t st = m->stream;
+  const int n = s->n;
+  memcpy(s->h_x0P0, state26, sizeof(double) * 26);
+  memcpy(s->h_x0P0 + 26, P, sizeof(double) * NDOF * NDOF);
+  CU(cudaMemcpyAsync(s->d_x0P0, s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF), cudaMemcpyHostToDevice, st));
+  k_esikf_begin<<<1, 256, 0, st>>>(s->ctl, s->d_x0P0, s->d_x0P0 + 26, n);
+  m->launches++;
+  for (int p = 0; p <= s->cfg.max_iterations; ++p) {
+    if (n > 0) {
+      {
+        ProfScope ps(m, FLB_K_KNN);
+        KnnArgs a;
+        a.m = m->d; a.q = nullptr; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
+        a.phase_stats = m->prof_on ? m->d_phase : nullptr;
+        a.ctl = s->ctl; a.body = s->body;
+        if (launch_knn<5>(m, a)) return 1;
+      }
+      {
+        ProfScope ps(m, FLB_K_RESIDUAL);
+        MeasArgs ma = meas_args(s, PoseDev{}, 0);
+        ma.ctl = s->ctl;
+        if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+        else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+        m->launches++;
+      }
+    }
+    {
+      ProfScope ps(m, FLB_K_REDUCE);
+      k_esikf_step<<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid);
+      m->launches++;
+    }
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(EsikfCtl), cudaMemcpyDeviceToHost, st));
+  s->have_pass = false;
+  return 0;
+}
+static void stats_from_ctl(const EsikfCtl* c, flb_update_stats* stats) {
+  if (!stats) return;
+  stats->passes = c->passes; stats->search_passes = c->searches; stats->effct_feat_num = c->lastM;
+  stats->converged_count = c->t; stats->total_residual = c->last_res;
+}
+
 extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_update_stats* stats) {
   if (!s || !state26 || !P) return set_err("flb_esikf_update: null argument");
   CU(cudaSetDevice(s->map->cfg.device));
-  return run_update(s, state26, P, stats);
+  if (!s->device_update) return run_update(s, state26, P, stats);
+  flb_map* m = s->map;
+  CU(cudaEventRecord(s->ev0, m->stream));
+  if (enqueue_update_device(s, state26, P)) return 1;
+  CU(cudaEventRecord(s->ev1, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  if (s->h_ctl->need_host) return run_update(s, state26, P, stats);  // M < 23: explicit-row branch on the host
+  memcpy(state26, s->h_ctl->x, sizeof(double) * 26);
+  memcpy(P, s->h_ctl->P, sizeof(double) * NDOF * NDOF);
+  stats_from_ctl(s->h_ctl, stats);
+  if (stats) CU(cudaEventElapsedTime(&stats->gpu_ms, s->ev0, s->ev1));
+  return 0;
 }
 
-static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited) {
+static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl = false) {
   flb_map* m = s->map;
   cudaStream_t st = m->stream;
   const int n = s->n;
   if (n <= 0) return 0;
-  const PoseDev pose = pose_from(state26);
+  const PoseDev pose = from_ctl ? PoseDev{} : pose_from(state26);
   CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
   {
     ProfScope ps(m, FLB_K_CLASSIFY);
-    k_classify<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->nbr, s->cnt, n, flg_EKF_inited,
-                                                                  s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
+    k_classify<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, from_ctl ? s->ctl : nullptr, s->body, s->nbr, s->cnt, n,
+                                                                  flg_EKF_inited, s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
     m->launches++;
   }
   CU(cudaGetLastError());
-  if (insert_device(m, s->world, s->cls, n, 2)) return 1;
+  if (insert_device(m, s->world, s->cls, n, 2, from_ctl ? &s->ctl->need_host : nullptr)) return 1;
   CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   return 0;
 }
@@ -1040,17 +1128,39 @@ extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* bo
     int nb = 0;
     if (flb_fov_segment(m, fov, fov->pos_lid, nullptr, &nb, &r.n_deleted)) return 1;
   }
-  if (run_update(s, state26, P, &r.update)) return 1;  // :2380
+  bool host_path = !s->device_update;
+  double prior_x[26], prior_P[NDOF * NDOF];
+  if (!host_path) {
+    memcpy(prior_x, state26, sizeof(prior_x));
+    memcpy(prior_P, P, sizeof(prior_P));
+    CU(cudaEventRecord(s->ev0, m->stream));
+    if (enqueue_update_device(s, state26, P)) return 1;   // :2380, all passes enqueued without host round trips
+    CU(cudaEventRecord(s->ev1, m->stream));
+    if (s->n > 0 && enqueue_map_incremental(s, state26, flg_EKF_inited, true)) return 1;  // :2401 with the device posterior
+    CU(cudaEventRecord(s->ev3, m->stream));
+    if (fetch_counters(m)) return 1;                       // the single synchronisation of the step
+    if (s->h_ctl->need_host) {
+      host_path = true;                                    // M < 23 branch: redo this scan on the host-driven path
+      memcpy(state26, prior_x, sizeof(prior_x));
+      memcpy(P, prior_P, sizeof(prior_P));
+    } else {
+      memcpy(state26, s->h_ctl->x, sizeof(double) * 26);
+      memcpy(P, s->h_ctl->P, sizeof(double) * NDOF * NDOF);
+      stats_from_ctl(s->h_ctl, &r.update);
+      CU(cudaEventElapsedTime(&r.update.gpu_ms, s->ev0, s->ev1));
+    }
+  }
+  if (host_path) {
+    if (run_update(s, state26, P, &r.update)) return 1;  // :2380
+    if (s->n > 0 && enqueue_map_incremental(s, state26, flg_EKF_inited)) return 1;  // :2401
+    CU(cudaEventRecord(s->ev3, m->stream));
+    if (fetch_counters(m)) return 1;
+  }
   if (fov) {  // :2383 pos_lid = pos + rot * offset_T_L_I
     host::State x = host::State::from26(state26);
     host::V3 pl = x.pos + host::rotate(x.rot, x.offT);
     for (int i = 0; i < 3; ++i) fov->pos_lid[i] = pl.a[i];
   }
-  if (s->n > 0) {  // :2401
-    if (enqueue_map_incremental(s, state26, flg_EKF_inited)) return 1;
-  }
-  CU(cudaEventRecord(s->ev3, m->stream));
-  if (fetch_counters(m)) return 1;
   r.n_to_add = s->n > 0 ? s->h_cnt2[0] : 0;
   r.n_no_downsample = s->n > 0 ? s->h_cnt2[1] : 0;
   r.map_valid = m->h_counters[CNT_VALID];

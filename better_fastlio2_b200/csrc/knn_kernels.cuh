@@ -96,6 +96,51 @@ __device__ __forceinline__ int warp_merge(TopK<K>& t, int lane, float& rd, float
   return gcount;
 }
 
+// K0: body -> world transform (laserMapping.cpp:1894-1898): double math (Eigen quaternion * vector form), result
+// rounded to float.  R = s.rot, Roff = s.offset_R_L_I.
+struct PoseDev {
+  double rot[4];   // x,y,z,w
+  double offR[4];
+  double pos[3];
+  double offT[3];
+};
+__device__ __forceinline__ void qrot_d(const double* q, double vx, double vy, double vz, double& ox, double& oy, double& oz) {
+  double ux = __dsub_rn(__dmul_rn(q[1], vz), __dmul_rn(q[2], vy));
+  double uy = __dsub_rn(__dmul_rn(q[2], vx), __dmul_rn(q[0], vz));
+  double uz = __dsub_rn(__dmul_rn(q[0], vy), __dmul_rn(q[1], vx));
+  ux = __dadd_rn(ux, ux); uy = __dadd_rn(uy, uy); uz = __dadd_rn(uz, uz);
+  const double cx = __dsub_rn(__dmul_rn(q[1], uz), __dmul_rn(q[2], uy));
+  const double cy = __dsub_rn(__dmul_rn(q[2], ux), __dmul_rn(q[0], uz));
+  const double cz = __dsub_rn(__dmul_rn(q[0], uy), __dmul_rn(q[1], ux));
+  ox = __dadd_rn(__dadd_rn(vx, __dmul_rn(q[3], ux)), cx);
+  oy = __dadd_rn(__dadd_rn(vy, __dmul_rn(q[3], uy)), cy);
+  oz = __dadd_rn(__dadd_rn(vz, __dmul_rn(q[3], uz)), cz);
+}
+__device__ __forceinline__ float4 body_to_world(const PoseDev& s, const float4 pb) {
+  double ax, ay, az, gx, gy, gz;
+  qrot_d(s.offR, (double)pb.x, (double)pb.y, (double)pb.z, ax, ay, az);
+  ax = __dadd_rn(ax, s.offT[0]); ay = __dadd_rn(ay, s.offT[1]); az = __dadd_rn(az, s.offT[2]);
+  qrot_d(s.rot, ax, ay, az, gx, gy, gz);
+  return make_float4((float)__dadd_rn(gx, s.pos[0]), (float)__dadd_rn(gy, s.pos[1]), (float)__dadd_rn(gz, s.pos[2]), pb.w);
+}
+
+// Device-resident state of the iterated update (see esikf_device.cuh); the measurement kernels read the pose of the
+// current iterate and the loop flags from here when running in device-driven mode (ctl != nullptr).
+constexpr int NDOF = 23;
+struct EsikfCtl {
+  double x[26];        // current iterate x_
+  double xp[26];       // x_propagated
+  double Pp[NDOF * NDOF];
+  double P[NDOF * NDOF];
+  double limit[NDOF];
+  double R;
+  double last_res;
+  PoseDev pose;        // pose of the current iterate
+  int max_iter, it, t, converge, finished, need_host, passes, searches, lastM, n;
+  int pad_[2];
+};
+__device__ __forceinline__ bool ctl_pass_active(const EsikfCtl* c) { return !c->finished && c->it < c->max_iter; }
+
 struct KnnArgs {
   MapDev m;
   const float4* q;     // n world-frame query points (x,y,z,*)
@@ -106,6 +151,8 @@ struct KnnArgs {
   int* phase_stats;    // optional [4]: queries finishing in phase A / B / C, total candidate points
   int* worklist;       // stencil kernel: indices of queries it could not prove complete; warp kernel: its input list
   int* work_count;     // number of entries in worklist (device)
+  const EsikfCtl* ctl; // device-driven mode: queries = body_to_world(ctl->pose, body[i]); skipped unless a search pass
+  const float4* body;
 };
 
 // visit every point of voxel slot `idx` (head + overflow chain)
@@ -177,10 +224,11 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   const float ds = m.ds;
   const float lim = a.max_d2;
+  if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
   const int nwork = a.worklist ? *a.work_count : a.n;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwork; w += warps_per_grid) {
     const int i = a.worklist ? a.worklist[w] : w;
-    const float4 q4 = __ldg(&a.q[i]);
+    const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     TopK<K> t;
     t.clear();
@@ -345,9 +393,10 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
   const int tid = threadIdx.x;
   const int i = blockIdx.x * blockDim.x + tid;
   if (i >= a.n) return;
+  if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
   const float ds = m.ds;
   const float lim = a.max_d2;
-  const float4 q4 = __ldg(&a.q[i]);
+  const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
   const float qx = q4.x, qy = q4.y, qz = q4.z;
   const float qlim = 4.0e6f * ds;
   TopKId<K> t;
@@ -424,33 +473,6 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
   }
 }
 
-// K0: body -> world transform (laserMapping.cpp:1894-1898): double math (Eigen quaternion * vector form), result
-// rounded to float.  R = s.rot, Roff = s.offset_R_L_I.
-struct PoseDev {
-  double rot[4];   // x,y,z,w
-  double offR[4];
-  double pos[3];
-  double offT[3];
-};
-__device__ __forceinline__ void qrot_d(const double* q, double vx, double vy, double vz, double& ox, double& oy, double& oz) {
-  double ux = __dsub_rn(__dmul_rn(q[1], vz), __dmul_rn(q[2], vy));
-  double uy = __dsub_rn(__dmul_rn(q[2], vx), __dmul_rn(q[0], vz));
-  double uz = __dsub_rn(__dmul_rn(q[0], vy), __dmul_rn(q[1], vx));
-  ux = __dadd_rn(ux, ux); uy = __dadd_rn(uy, uy); uz = __dadd_rn(uz, uz);
-  const double cx = __dsub_rn(__dmul_rn(q[1], uz), __dmul_rn(q[2], uy));
-  const double cy = __dsub_rn(__dmul_rn(q[2], ux), __dmul_rn(q[0], uz));
-  const double cz = __dsub_rn(__dmul_rn(q[0], uy), __dmul_rn(q[1], ux));
-  ox = __dadd_rn(__dadd_rn(vx, __dmul_rn(q[3], ux)), cx);
-  oy = __dadd_rn(__dadd_rn(vy, __dmul_rn(q[3], uy)), cy);
-  oz = __dadd_rn(__dadd_rn(vz, __dmul_rn(q[3], uz)), cz);
-}
-__device__ __forceinline__ float4 body_to_world(const PoseDev& s, const float4 pb) {
-  double ax, ay, az, gx, gy, gz;
-  qrot_d(s.offR, (double)pb.x, (double)pb.y, (double)pb.z, ax, ay, az);
-  ax = __dadd_rn(ax, s.offT[0]); ay = __dadd_rn(ay, s.offT[1]); az = __dadd_rn(az, s.offT[2]);
-  qrot_d(s.rot, ax, ay, az, gx, gy, gz);
-  return make_float4((float)__dadd_rn(gx, s.pos[0]), (float)__dadd_rn(gy, s.pos[1]), (float)__dadd_rn(gz, s.pos[2]), pb.w);
-}
 __global__ void k_transform(PoseDev s, const float4* __restrict__ body, float4* __restrict__ world, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) world[i] = body_to_world(s, body[i]);
 }

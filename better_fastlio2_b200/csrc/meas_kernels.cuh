@@ -176,6 +176,8 @@ struct MeasArgs {
   double* partial;            // [gridDim.x][NACC]
   int n;
   int search;                 // ekfom_data.converge
+  const EsikfCtl* ctl;        // device-driven mode: pose / search flag / early exit come from here
+  float4* world_out;          // device-driven mode: feats_down_world is produced here (no separate K0)
 };
 
 __constant__ unsigned char c_tri_i[91];
@@ -213,9 +215,9 @@ __device__ __forceinline__ void jacobian_row(const PoseDev& s, const float4 pb, 
 }
 
 // Stage A of h_share_model for one point (laserMapping.cpp:1903-1938). Returns selected flag; fills nv.
-__device__ __forceinline__ bool select_point(const MeasArgs& a, int i, float4& nv) {
+__device__ __forceinline__ bool select_point(const MeasArgs& a, int i, int search, const float4 pw, float4& nv) {
   bool sel;
-  if (a.search) {
+  if (search) {
     const int c = a.cnt[i];
     const float d4 = a.nbr[(size_t)4 * a.n + i].w;
     sel = (c < 5) ? false : (d4 > 5.f ? false : true);        // :1911
@@ -231,7 +233,6 @@ __device__ __forceinline__ bool select_point(const MeasArgs& a, int i, float4& n
   }
   float pa, pb_, pc, pd;
   if (!esti_plane_dev(P, 0.1f, pa, pb_, pc, pd)) return false;
-  const float4 pw = a.world[i];
   const float4 pb = a.body[i];
   const float pd2 = pa * pw.x + pb_ * pw.y + pc * pw.z + pd;  // :1925 (float, left to right)
   const double bn = sqrt((double)pb.x * (double)pb.x + (double)pb.y * (double)pb.y + (double)pb.z * (double)pb.z);
@@ -254,6 +255,9 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
   for (int e = 0; e < EPL; ++e) acc[e] = 0.0;
   double rsum = 0.0;
   int msum = 0;
+  if (a.ctl && !ctl_pass_active(a.ctl)) return;   // the iterated update already finished (block-uniform)
+  const PoseDev pose = a.ctl ? a.ctl->pose : a.pose;
+  const int search = a.ctl ? a.ctl->converge : a.search;
   const int stride = gridDim.x * blockDim.x;
   const int nround = (a.n + stride - 1) / stride;
   for (int it = 0; it < nround; ++it) {
@@ -261,12 +265,15 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
     float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
     bool sel = false;
     if (i < a.n) {
-      sel = select_point(a, i, nv);
+      float4 pw;
+      if (a.ctl) { pw = body_to_world(pose, a.body[i]); a.world_out[i] = pw; }
+      else pw = a.world[i];
+      sel = select_point(a, i, search, pw, nv);
       a.sel[i] = sel ? 1 : 0;
       if (sel) a.normvec[i] = nv;
     }
     double row[13];
-    if (sel) jacobian_row<EXTR>(a.pose, a.body[i], nv, row);
+    if (sel) jacobian_row<EXTR>(pose, a.body[i], nv, row);
     const unsigned any = __ballot_sync(FULL, sel);
     if (any == 0u) continue;
     if (EXTR) {
@@ -365,9 +372,11 @@ __global__ void k_sel_to_int(const unsigned char* __restrict__ sel, int* __restr
 // ---------------------------------------------------------------------------------------------- map_incremental classifier
 // laserMapping.cpp:1440-1490. cls: 0 dropped, 1 PointToAdd (downsample), 2 PointNoNeedDownsample.
 // counts[0] += #ToAdd, counts[1] += #NoNeed.
-__global__ void k_classify(PoseDev s, const float4* __restrict__ body, const float4* __restrict__ nbr,
+__global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __restrict__ body, const float4* __restrict__ nbr,
                            const unsigned char* __restrict__ cnt, int n, int flg_EKF_inited, double fs,
                            float4* __restrict__ world, unsigned char* __restrict__ cls, int* counts) {
+  if (ctl && ctl->need_host) return;  // the host fallback redoes update + insert for this scan
+  const PoseDev s = ctl ? ctl->pose : s_in;
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * blockDim.x;
   const int nround = (n + stride - 1) / stride;

@@ -158,6 +158,12 @@ typedef struct flb_update_stats {
  * hold the propagated state in and the posterior out. */
 int flb_esikf_update(flb_session* s, double* state26, double* P, flb_update_stats* stats);
 
+/* Update engine: 1 (default) = device-driven — all passes of the iterated update are enqueued up front and the
+ * 23-DOF algebra runs in a device kernel (no host round trip inside a scan); 0 = host-driven — the reference's
+ * structure, one synchronisation per pass with the algebra in C++ on the host.  Both give the same result to ~1e-15;
+ * the device engine falls back to the host one for the under-determined M < 23 branch (esekfom.hpp:1720-1750). */
+int flb_session_set_update_engine(flb_session* s, int device_driven);
+
 /* map_incremental (laserMapping.cpp:1440-1496) with the posterior state: classify every scan point with the cached
  * neighbours, then Add_Points(PointToAdd,true) and Add_Points(PointNoNeedDownsample,false). */
 int flb_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, int* n_to_add, int* n_no_downsample);

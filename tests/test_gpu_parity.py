@@ -265,3 +265,53 @@ def test_closed_loop_sequence(oracle):
     print("closed loop max |d| =", maxd)
     ses.close()
     t.close()
+
+
+def test_update_engines_agree(scene, oracle):
+    """Device-driven engine (ESIKF algebra in k_esikf_step, no host round trips) vs host-driven engine."""
+    t = _tree(scene)
+    out = {}
+    for dev in (True, False):
+        ses = capi.Session(t, max_scan_points=len(scene["body"]), max_iterations=3)
+        ses.set_update_engine(dev)
+        ses.scan_upload(scene["body"])
+        s, P, st = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
+        out[dev] = (s, P, st, ses.neighbors())
+        ses.close()
+    (s1, P1, st1, nb1), (s0, P0, st0, nb0) = out[True], out[False]
+    for k in ("passes", "search_passes", "effct_feat_num", "converged_count"):
+        assert st1[k] == st0[k], k
+    assert np.abs(s1 - s0).max() < 1e-11
+    assert np.allclose(P1, P0, rtol=1e-7, atol=1e-14)
+    assert np.array_equal(nb1["d2"], nb0["d2"]) and np.array_equal(nb1["sel"], nb0["sel"])
+    assert np.array_equal(nb1["world"], nb0["world"])
+    t.close()
+
+
+def test_underdetermined_and_invalid_passes(scene, oracle):
+    """M < 23 takes the explicit-row branch (esekfom.hpp:1720-1750); M < 1 skips the pass (valid=false)."""
+    t = _tree(scene)
+    ref = oracle.make_map(ds=scene["ds"])
+    ref.Build(scene["map"])
+    few = scene["body"][:: max(1, len(scene["body"]) // 14)][:14]
+    for dev in (True, False):
+        ses = capi.Session(t, max_scan_points=64, max_iterations=3)
+        ses.set_update_engine(dev)
+        ses.scan_upload(few)
+        s_g, P_g, st = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
+        s_c, P_c, sc, st_c, _ = oracle.esikf_update(scene["prior"], scene["P"], few, ref, max_iter=3)
+        assert 0 < st["effct_feat_num"] < 23 and st["effct_feat_num"] == st_c[2]
+        assert np.abs(s_g - s_c).max() < 1e-8
+        assert np.allclose(P_g, P_c, rtol=1e-6, atol=1e-12)
+        # a scan far away from every map point: every pass invalid, state and covariance untouched
+        far = (few + np.array([0, 0, 500.0], np.float32)).astype(np.float32)
+        ses.scan_upload(far)
+        s2, P2, st2 = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
+        assert st2["effct_feat_num"] == 0 and st2["passes"] == 4
+        assert np.array_equal(s2, scene["prior"]) and np.array_equal(P2, scene["P"])
+        # empty scan
+        ses.scan_upload(np.zeros((0, 3), np.float32))
+        s3, P3, st3 = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
+        assert np.array_equal(s3, scene["prior"])
+        ses.close()
+    t.close()
