@@ -12,6 +12,8 @@ namespace flb {
 
 namespace dev {
 
+constexpr int ESIKF_THREADS = 256;
+
 __device__ __forceinline__ void qmul(const double* a, const double* b, double* r) {  // (x,y,z,w)
   const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
   const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
@@ -55,7 +57,7 @@ __device__ __forceinline__ void log_quat(const double* q, double* r) {  // SOn.h
   const double s = 2.0 / nv * atan(nv / q[3]);
   r[0] = s * q[0]; r[1] = s * q[1]; r[2] = s * q[2];
 }
-__device__ __forceinline__ void A_matrix_T(const double* v, double* J) {  // A_matrix(v)^T, mtkmath.hpp:235-247
+__device__ __noinline__ void A_matrix_T(const double* v, double* J) {  // A_matrix(v)^T, mtkmath.hpp:235-247
   const double sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
   const double n = sqrt(sq);
   double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -80,6 +82,60 @@ __device__ __forceinline__ void s2_Bx(const double* vec, double* Bx) {  // S2.hp
     Bx[3] = -1; Bx[4] = 1;
   }
 }
+// Nx_yy(xg) (2x3, S2.hpp:259-264) and Mx(xpg, delta) (3x2, S2.hpp:266-280) separately, so two warps can build them
+__device__ __noinline__ void s2_Nx(const double* xg, double* Nx) {
+  const double len = 98090.0 / 10000.0;
+  double Bx[6], H[9];
+  s2_Bx(xg, Bx);
+  hat(xg, H);
+  const double sc = 1 / len / len;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += (sc * Bx[2 * k + i]) * H[3 * k + j]; Nx[3 * i + j] = s; }
+}
+__device__ __noinline__ void s2_Mx(const double* xpg, const double* delta, double* Mx) {
+  double Bp[6], Hp[9];
+  s2_Bx(xpg, Bp);
+  hat(xpg, Hp);
+  const double dn = sqrt(delta[0] * delta[0] + delta[1] * delta[1]);
+  if (dn < 1e-11) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += (-Hp[3 * i + k]) * Bp[2 * k + j]; Mx[2 * i + j] = s; }
+  } else {
+    double Bu[3];
+    for (int i = 0; i < 3; ++i) Bu[i] = Bp[2 * i] * delta[0] + Bp[2 * i + 1] * delta[1];
+    double q[4], E[9], At[9], T1[9], T2[9];
+    exp_quat(Bu, 0.0, q);  // scalar(1/2) == 0 in the reference (S2.hpp:277)
+    rotmat(q, E);
+    A_matrix_T(Bu, At);
+    for (int i = 0; i < 9; ++i) E[i] = -E[i];
+    mm3(E, Hp, T1);
+    mm3(T1, At, T2);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += T2[3 * i + k] * Bp[2 * k + j]; Mx[2 * i + j] = s; }
+  }
+}
+// Gauss-Jordan inverse of a symmetric positive definite 23x23 matrix in shared memory, block-wide and COMPACT (a
+// rolled 23-sweep loop: this kernel runs once per launch, so straight-line unrolled code would be instruction-fetch
+// bound).  No pivoting is needed for SPD input (both matrices inverted per pass are: P/R and (P/R)^-1 + H^T H).
+// Ping-pong between buf0 and buf1 (one barrier per sweep); the result ends in buf1 (23 is odd).
+__device__ __noinline__ void b_inverse_spd(double* buf0, double* buf1, int tid) {
+  double* cur = buf0;
+  double* nxt = buf1;
+#pragma unroll 1
+  for (int k = 0; k < NDOF; ++k) {
+    const double inv = 1.0 / cur[k * NDOF + k];
+#pragma unroll 1
+    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) {
+      const int i = e / NDOF, j = e - i * NDOF;
+      double v;
+      if (i == k) v = (j == k) ? inv : cur[k * NDOF + j] * inv;
+      else if (j == k) v = -(cur[i * NDOF + k] * inv);
+      else v = cur[e] - cur[i * NDOF + k] * (cur[k * NDOF + j] * inv);
+      nxt[e] = v;
+    }
+    __syncthreads();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+}
+
 // J (2x2) = Nx_yy(xg) * Mx(xpg, delta)   (S2.hpp:259-280, esekfom.hpp:1693-1695)
 __device__ __forceinline__ void s2_jac(const double* xg, const double* xpg, const double* delta, double* J) {
   const double len = 98090.0 / 10000.0;
@@ -153,17 +209,17 @@ __device__ __forceinline__ void state_boxminus(const double* x, const double* o,
   }
 }
 // ---- piecewise versions so that independent sub-manifolds are handled by different warps concurrently
-__device__ __forceinline__ void so3_boxminus(const double* xq, const double* oq, double* r) {  // log(o^-1 * x)
+__device__ __noinline__ void so3_boxminus(const double* xq, const double* oq, double* r) {  // log(o^-1 * x)
   double qc[4] = {-oq[0], -oq[1], -oq[2], oq[3]}, q[4];
   qmul(qc, xq, q);
   log_quat(q, r);
 }
-__device__ __forceinline__ void so3_boxplus(double* xq, const double* d) {
+__device__ __noinline__ void so3_boxplus(double* xq, const double* d) {
   double q[4];
   exp_quat(d, 0.5, q);
   qmul(xq, q, xq);
 }
-__device__ __forceinline__ void s2_boxminus(const double* v, const double* ov, double* r) {  // S2.hpp:144-167
+__device__ __noinline__ void s2_boxminus(const double* v, const double* ov, double* r) {  // S2.hpp:144-167
   double H[9], t[3];
   hat(v, H);
   for (int i = 0; i < 3; ++i) t[i] = H[3 * i] * ov[0] + H[3 * i + 1] * ov[1] + H[3 * i + 2] * ov[2];
@@ -182,7 +238,7 @@ __device__ __forceinline__ void s2_boxminus(const double* v, const double* ov, d
     for (int i = 0; i < 2; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += (f * Bx[2 * k + i]) * u[k]; r[i] = s; }
   }
 }
-__device__ __forceinline__ void s2_boxplus(double* v, const double* d) {  // S2.hpp:136-142
+__device__ __noinline__ void s2_boxplus(double* v, const double* d) {  // S2.hpp:136-142
   double Bx[6], Bu[3], R[9], o[3], q[4];
   s2_Bx(v, Bx);
   for (int i = 0; i < 3; ++i) Bu[i] = Bx[2 * i] * d[0] + Bx[2 * i + 1] * d[1];
@@ -198,7 +254,6 @@ __device__ __forceinline__ void pose_from_state(const double* x, PoseDev& p) {
 
 // ---- block-cooperative 23x23 helpers on shared memory (row-major, leading dimension NDOF); every thread of the
 // block calls them (they contain __syncthreads)
-constexpr int ESIKF_THREADS = 256;
 // rows [idx, idx+D) of Dst <- J * rows of Src
 template <int D>
 __device__ __forceinline__ void b_mul_rows(double* Dst, const double* Src, int idx, const double* J, int tid) {
@@ -264,64 +319,47 @@ __device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double*
 }  // namespace dev
 
 // Load the propagated state / covariance for a new scan.
-__global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ x0, const double* __restrict__ P0, int n) {
+// staging layout: x0[26] | P0[529] | n | flg_EKF_inited   (all doubles, so one H2D copy carries a scan's inputs)
+__global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage) {
+  const double* x0 = stage;
+  const double* P0 = stage + 26;
+  const int n = (int)stage[26 + NDOF * NDOF];
   for (int i = threadIdx.x; i < NDOF * NDOF; i += blockDim.x) { c->Pp[i] = P0[i]; c->P[i] = P0[i]; }
   if (threadIdx.x < 26) { c->x[threadIdx.x] = x0[threadIdx.x]; c->xp[threadIdx.x] = x0[threadIdx.x]; }
   __syncthreads();
   if (threadIdx.x == 0) {
     c->it = -1; c->t = 0; c->converge = 1; c->finished = 0; c->need_host = 0; c->passes = 0; c->searches = 0;
-    c->lastM = 0; c->last_res = 0.0; c->n = n;
+    c->lastM = 0; c->last_res = 0.0; c->n = n; c->flg_inited = (int)stage[26 + NDOF * NDOF + 1];
     dev::pose_from_state(c->x, c->pose);
   }
 }
 
-// One loop iteration of update_iterated_dyn_share_modified after the measurement pass wrote its block partials.
-__global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_step(EsikfCtl* c, const double* __restrict__ partial, int nblocks) {
+// One loop iteration of update_iterated_dyn_share_modified is split in two kernels so that the half that only needs
+// the current iterate overlaps with the measurement kernels of the same pass (second stream / graph branch):
+//   k_esikf_pre  : dx = x [-] x_prop, projection Jacobians, projected P and (P/R)^-1            (esekfom.hpp:1655-1703,1788)
+//   k_esikf_post : reduce the block partials, + H^T H, second inverse, K, dx_, boxplus, convergence bookkeeping and
+//                  the final covariance                                                        (:1790-1935)
+// Both are latency-oriented: loop flags / state staged in shared memory with parallel loads, transcendental-heavy
+// sub-manifold work spread over warps, compact rolled loops (a kernel that runs once per launch is instruction-fetch
+// bound on straight-line code).
+struct EsikfScratch {
+  double dxn[NDOF];
+  double P[NDOF * NDOF];   // projected P_propagated
+  double T[NDOF * NDOF];   // (P/R)^-1
+};
+
+__global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl* c, EsikfScratch* sc) {
   using namespace dev;
-  __shared__ double acc[NACC];
-  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[NDOF * NDOF], aug[2 * NDOF * 2 * NDOF];
-  __shared__ double Kx[NDOF * 12], HTH[144], HTh[12], Kh[NDOF];
-  __shared__ double dx[NDOF], dxn[NDOF], dx_[NDOF], J3a[9], J3b[9], J2[4], xs[26], xps[26];
-  __shared__ int s_go, s_fin, s_conv, s_tt;
+  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[NDOF * NDOF];
+  __shared__ double dx[NDOF], J3a[9], J3b[9], J2[4], Nx[6], Mx[6], xs[26], xps[26];
   const int tid = threadIdx.x;
-  if (tid == 0) s_go = (!c->finished && c->it < c->max_iter && c->n > 0) ? 1 : 0;
-  __syncthreads();
-  if (!s_go) {
-    // loop already ended; an empty scan still consumes its passes (every pass invalid)
-    if (tid == 0 && !c->finished && c->it < c->max_iter && c->n <= 0) { c->it++; c->passes++; }
-    return;
-  }
-  // ---- fixed-order reduction of the per-block partials (role of K2): 2 threads per entry, halves combined in order
-  {
-    const int e = tid >> 1, h = tid & 1;
-    double s = 0.0;
-    if (e < NACC) {
-      const int half = (nblocks + 1) >> 1;
-      const int b0 = h ? half : 0, b1 = h ? nblocks : half;
-      for (int b = b0; b < b1; ++b) s += partial[(size_t)b * NACC + e];
-    }
-    const double o = __shfl_xor_sync(FULL, s, 1);
-    if (e < NACC && h == 0) acc[e] = s + o;
-  }
-  __syncthreads();
-  const int M = (int)(acc[92] + 0.5);
-  if (tid == 0) { c->passes++; if (c->converge) c->searches++; }
-  if (M < 1) { if (tid == 0) c->it++; return; }                                   // valid = false -> continue (:1641-1644)
-  if (M < NDOF) { if (tid == 0) { c->need_host = 1; c->finished = 1; } return; }  // under-determined branch: host path
-  const double R = c->R;
-  const int it = c->it, max_iter = c->max_iter;
-  if (tid < 144) {
-    const int i = tid / 12, j = tid - i * 12;
-    const int a = i < j ? i : j, b = i < j ? j : i;
-    HTH[tid] = acc[a * 13 - a * (a - 1) / 2 + (b - a)];
-  }
-  if (tid >= 160 && tid < 172) { const int l = tid - 160; HTh[l] = acc[l * 13 - l * (l - 1) / 2 + (12 - l)]; }
-  if (tid >= 192 && tid < 218) { xs[tid - 192] = c->x[tid - 192]; xps[tid - 192] = c->xp[tid - 192]; }
+  if (c->finished || c->it >= c->max_iter || c->n <= 0) return;   // uniform
+  if (tid >= 32 && tid < 58) { xs[tid - 32] = c->x[tid - 32]; xps[tid - 32] = c->xp[tid - 32]; }
   for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) P[e] = c->Pp[e];
+  const double R = c->R;
   __syncthreads();
   // x_ [-] x_propagated (:1655) and the projection Jacobians, one sub-manifold per warp
   if (tid == 0) {
-    c->lastM = M; c->last_res = acc[91];
     so3_boxminus(xs + 3, xps + 3, dx + 3);
     A_matrix_T(dx + 3, J3a);
   } else if (tid == 32) {
@@ -329,35 +367,93 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_step(EsikfCtl* c, 
     A_matrix_T(dx + 6, J3b);
   } else if (tid == 64) {
     s2_boxminus(xs + 23, xps + 23, dx + 21);
-    s2_jac(xs + 23, xps + 23, dx + 21, J2);
+    s2_Mx(xps + 23, dx + 21, Mx);
   } else if (tid == 96) {
+    s2_Nx(xs + 23, Nx);
+  } else if (tid == 128) {
     for (int i = 0; i < 3; ++i) {
       dx[i] = xs[i] - xps[i]; dx[9 + i] = xs[11 + i] - xps[11 + i]; dx[12 + i] = xs[14 + i] - xps[14 + i];
       dx[15 + i] = xs[17 + i] - xps[17 + i]; dx[18 + i] = xs[20 + i] - xps[20 + i];
     }
   }
   __syncthreads();
+  if (tid < 4) { const int i = tid >> 1, j = tid & 1; double s = 0; for (int k = 0; k < 3; ++k) s += Nx[3 * i + k] * Mx[2 * k + j]; J2[tid] = s; }
+  __syncthreads();
   if (tid < NDOF) {                                     // dx_new with the SO3 / S2 blocks projected (:1671, :1696)
     double v = dx[tid];
     if (tid >= 3 && tid < 6) { const int i = tid - 3; v = J3a[3 * i] * dx[3] + J3a[3 * i + 1] * dx[4] + J3a[3 * i + 2] * dx[5]; }
     else if (tid >= 6 && tid < 9) { const int i = tid - 6; v = J3b[3 * i] * dx[6] + J3b[3 * i + 1] * dx[7] + J3b[3 * i + 2] * dx[8]; }
     else if (tid >= 21) { const int i = tid - 21; v = J2[2 * i] * dx[21] + J2[2 * i + 1] * dx[22]; }
-    dxn[tid] = v;
+    sc->dxn[tid] = v;
   }
-  __syncthreads();
   b_mul_rows<3>(P, P, 3, J3a, tid);                     // SO3 blocks :1665-1681
   b_mul_cols_T<3>(P, 3, J3a, tid);
   b_mul_rows<3>(P, P, 6, J3b, tid);
   b_mul_cols_T<3>(P, 6, J3b, tid);
   b_mul_rows<2>(P, P, 21, J2, tid);                     // S2 block :1683-1703
   b_mul_cols_T<2>(P, 21, J2, tid);
-  // information form :1788-1815
-  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) L[e] = P[e] / R;
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) { L[e] = P[e] / R; sc->P[e] = P[e]; }
   __syncthreads();
-  b_inverse(L, T, aug, tid);                            // (P/R)^-1
+  b_inverse_spd(L, T, tid);                             // (P/R)^-1 -> T   (:1788)
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) sc->T[e] = T[e];
+}
+
+__global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, const double* __restrict__ partial, int nblocks,
+                                                                    const EsikfScratch* __restrict__ sc) {
+  using namespace dev;
+  __shared__ double acc[96];
+  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[NDOF * NDOF];
+  __shared__ double Kx[NDOF * 12], HTH[144], HTh[12], Kh[NDOF], lim[NDOF];
+  __shared__ double dxn[NDOF], dx_[NDOF], J3a[9], J3b[9], J2[4], Nx[6], Mx[6], xs[26], xps[26];
+  __shared__ int s_i[8];   // finished, it, max_iter, n, t, converge
+  __shared__ int s_fin, s_conv, s_tt;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_i[0] = c->finished; else if (tid == 1) s_i[1] = c->it; else if (tid == 2) s_i[2] = c->max_iter;
+  else if (tid == 3) s_i[3] = c->n; else if (tid == 4) s_i[4] = c->t; else if (tid == 5) s_i[5] = c->converge;
+  if (tid >= 32 && tid < 58) { xs[tid - 32] = c->x[tid - 32]; xps[tid - 32] = c->xp[tid - 32]; }
+  if (tid >= 64 && tid < 64 + NDOF) { lim[tid - 64] = c->limit[tid - 64]; dxn[tid - 64] = sc->dxn[tid - 64]; }
+  // ---- fixed-order reduction of the per-block partials (role of K2): 2 threads per entry (halves of the block range),
+  // 16 independent loads in flight per thread
+  {
+    const int e = tid >> 1, h = tid & 1;
+    double s = 0.0;
+    if (e < NACC) {
+      const int half = (nblocks + 1) >> 1;
+      const int b0 = h ? half : 0, b1 = h ? nblocks : half;
+      int b = b0;
+      for (; b + 16 <= b1; b += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = partial[(size_t)(b + u) * NACC + e];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+      }
+      for (; b < b1; ++b) s += partial[(size_t)b * NACC + e];
+    }
+    const double o = __shfl_xor_sync(FULL, s, 1);
+    if (e < NACC && h == 0) acc[e] = s + o;
+  }
+  __syncthreads();
+  const int it = s_i[1], max_iter = s_i[2];
+  if (s_i[0] || it >= max_iter) return;                                          // loop already ended
+  if (s_i[3] <= 0) { if (tid == 0) { c->it = it + 1; c->passes++; } return; }    // empty scan: every pass invalid
+  const int M = (int)(acc[92] + 0.5);
+  if (tid == 0) { c->passes++; if (s_i[5]) c->searches++; }
+  if (M < 1) { if (tid == 0) c->it = it + 1; return; }                            // valid = false -> continue (:1641-1644)
+  if (M < NDOF) { if (tid == 0) { c->need_host = 1; c->finished = 1; } return; }  // under-determined branch: host path
+  if (tid == 0) { c->lastM = M; c->last_res = acc[91]; }
+  if (tid < 144) {
+    const int i = tid / 12, j = tid - i * 12;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    HTH[tid] = acc[a * 13 - a * (a - 1) / 2 + (b - a)];
+  }
+  if (tid >= 160 && tid < 172) { const int l = tid - 160; HTh[l] = acc[l * 13 - l * (l - 1) / 2 + (12 - l)]; }
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) { P[e] = sc->P[e]; T[e] = sc->T[e]; }
+  __syncthreads();
+  // information form :1790-1815
   if (tid < 144) T[(tid / 12) * NDOF + (tid % 12)] += HTH[tid];
   __syncthreads();
-  b_inverse(T, L, aug, tid);                            // P_inv -> L
+  b_inverse_spd(T, L, tid);                             // P_inv -> L
   if (tid < NDOF) { double s = 0; for (int k = 0; k < 12; ++k) s += L[tid * NDOF + k] * HTh[k]; Kh[tid] = s; }
   for (int e = tid; e < NDOF * 12; e += ESIKF_THREADS) {
     const int i = e / 12, b = e - i * 12;
@@ -372,26 +468,33 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_step(EsikfCtl* c, 
     dx_[tid] = Kh[tid] + s;
   }
   __syncthreads();
-  // x_ [+] dx_ (:1823), convergence test (:1824-1838) and the Jacobians of the final covariance, per sub-manifold
+  // convergence test (:1824-1838) first: the Jacobians of the final covariance are only needed on the last pass
   if (tid == 0) {
-    so3_boxplus(xs + 3, dx_ + 3);
-    A_matrix_T(dx_ + 3, J3a);
-  } else if (tid == 32) {
-    so3_boxplus(xs + 7, dx_ + 6);
-    A_matrix_T(dx_ + 6, J3b);
-  } else if (tid == 64) {
-    s2_boxplus(xs + 23, dx_ + 21);
-    s2_jac(xs + 23, xps + 23, dx_ + 21, J2);
-  } else if (tid == 96) {
-    for (int i = 0; i < 3; ++i) { xs[i] += dx_[i]; xs[11 + i] += dx_[9 + i]; xs[14 + i] += dx_[12 + i]; xs[17 + i] += dx_[15 + i]; xs[20 + i] += dx_[18 + i]; }
-  } else if (tid == 128) {
-    int conv = 1, tt = c->t;
-    for (int i = 0; i < NDOF; ++i) if (fabs(dx_[i]) > c->limit[i]) { conv = 0; break; }
+    int conv = 1, tt = s_i[4];
+    for (int i = 0; i < NDOF; ++i) if (fabs(dx_[i]) > lim[i]) { conv = 0; break; }
     if (conv) ++tt;
     if (!tt && it == max_iter - 2) conv = 1;            // :1835-1838
     s_conv = conv; s_tt = tt;
     s_fin = (tt > 1 || it == max_iter - 1) ? 1 : 0;
   }
+  __syncthreads();
+  // x_ [+] dx_ (:1823) per sub-manifold (+ Jacobians when finishing)
+  if (tid == 0) {
+    so3_boxplus(xs + 3, dx_ + 3);
+    if (s_fin) A_matrix_T(dx_ + 3, J3a);
+  } else if (tid == 32) {
+    so3_boxplus(xs + 7, dx_ + 6);
+    if (s_fin) A_matrix_T(dx_ + 6, J3b);
+  } else if (tid == 64) {
+    s2_boxplus(xs + 23, dx_ + 21);
+    if (s_fin) s2_Nx(xs + 23, Nx);
+  } else if (tid == 96) {
+    if (s_fin) s2_Mx(xps + 23, dx_ + 21, Mx);
+  } else if (tid == 128) {
+    for (int i = 0; i < 3; ++i) { xs[i] += dx_[i]; xs[11 + i] += dx_[9 + i]; xs[14 + i] += dx_[12 + i]; xs[17 + i] += dx_[15 + i]; xs[20 + i] += dx_[18 + i]; }
+  }
+  __syncthreads();
+  if (tid < 4 && s_fin) { const int i = tid >> 1, j = tid & 1; double s = 0; for (int k = 0; k < 3; ++k) s += Nx[3 * i + k] * Mx[2 * k + j]; J2[tid] = s; }
   __syncthreads();
   const int fin = s_fin;
   if (fin) {                                            // :1841-1931
@@ -427,10 +530,8 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_step(EsikfCtl* c, 
     for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) c->P[e] = P[e];  // P_ as last assigned (projected P_propagated)
   }
   if (tid < 26) c->x[tid] = xs[tid];
-  if (tid == 0) {
-    c->converge = s_conv; c->t = s_tt; c->finished = fin; c->it = it + 1;
-    pose_from_state(xs, c->pose);
-  }
+  if (tid == 32) { c->converge = s_conv; c->t = s_tt; c->finished = fin; c->it = it + 1; }
+  if (tid == 64) pose_from_state(xs, c->pose);
 }
 
 }  // namespace flb

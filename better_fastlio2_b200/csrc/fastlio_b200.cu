@@ -79,6 +79,7 @@ struct flb_map {
   int launches = 0;              // kernel launch counter (cumulative)
   // optional per-kernel-class CUDA-event timing (flb_map_profile_*)
   bool prof_on = false;
+  bool capturing = false;        // inside cudaStreamBeginCapture: no event timing, no allocations
   struct ProfRec { cudaEvent_t a, b; int cls; int nlaunch; };
   std::vector<ProfRec> prof_pool;
   size_t prof_used = 0;
@@ -90,7 +91,7 @@ struct flb_map {
 struct ProfScope {
   flb_map* m; flb_map::ProfRec* r = nullptr; int l0;
   ProfScope(flb_map* m_, int cls) : m(m_), l0(m_->launches) {
-    if (!m->prof_on) return;
+    if (!m->prof_on || m->capturing) return;
     if (m->prof_used == m->prof_pool.size()) {
       flb_map::ProfRec n{};
       if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
@@ -268,29 +269,31 @@ static int maybe_rehash(flb_map* m);
 
 // Insert device points. mode 0: verbatim (Build / Add_Points(false)); 1: downsample (Add_Points(true));
 // 2: classified (map_incremental: cls 1 -> downsample, cls 2 -> verbatim). Asynchronous on m->stream.
-static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode, const int* skip = nullptr) {
+static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode, const int* skip = nullptr,
+                         const int* n_dev = nullptr) {
+  // n_dev != nullptr: n is an upper bound (capacity) used for launch geometry, the real count is read on the device
   if (n <= 0) return 0;
   const int g = grid_for(n, 256, m->sm_count * 8);
   cudaStream_t st = m->stream;
   const unsigned char* c = (mode == 2) ? cls : nullptr;
   ProfScope ps(m, FLB_K_INSERT);
-  k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n, skip);
+  k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n, skip, n_dev);
   m->launches++;
   if (mode == 1 || mode == 2) {
     if (ensure_scratch(m, n)) return 1;
     const uint32_t sc = next_pow2((uint64_t)std::max(n, 512) * 2);
     CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
     CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
-    k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip);
-    k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip);
+    k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
+    k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
     m->launches += 2;
   }
   if (mode == 0 || mode == 2) {
-    k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip);
+    k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip, n_dev);
     m->launches++;
   }
   CU(cudaGetLastError());
-  m->has_root = true;
+  if (!n_dev) m->has_root = true;
   return 0;
 }
 
@@ -413,6 +416,7 @@ static int launch_knn(flb_map* m, KnnArgs a) {
   }
   a.worklist = m->worklist;
   a.work_count = m->d_misc + 12;
+  if (a.stride <= 0) a.stride = a.n;
   CU(cudaMemsetAsync(a.work_count, 0, sizeof(int), m->stream));
   k_knn_stencil<K><<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
   // the fallback grid is sized for the typical <2 % unresolved share; it loops over the list
@@ -447,7 +451,7 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
   a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt;
   a.max_d2 = (max_dist > 0.f && max_dist < 1e18f) ? max_dist * max_dist : INFINITY;
   a.phase_stats = nullptr;
-  a.ctl = nullptr; a.body = nullptr;
+  a.ctl = nullptr; a.body = nullptr; a.stride = nq;
   int lrc = (K == 5) ? launch_knn<5>(m, a) : launch_knn<20>(m, a);
   cudaError_t le = lrc ? cudaErrorUnknown : cudaGetLastError();
   std::vector<float4> h((size_t)nq * K);
@@ -619,6 +623,12 @@ struct flb_session {
   double* d_x0P0 = nullptr;      // device staging of the propagated state (26) + covariance (529)
   double* h_x0P0 = nullptr;      // pinned
   bool device_update = true;
+  EsikfScratch* d_scr = nullptr;
+  cudaStream_t side = nullptr;   // second stream: k_esikf_pre overlaps the measurement kernels of the same pass
+  cudaEvent_t ev_fork[8] = {nullptr}, ev_join[8] = {nullptr};
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [0] update only, [1] update + map_incremental
+  int graph_kernels[2] = {0, 0};
+  bool use_graph = true;
 };
 
 extern "C" void flb_session_default_config(flb_session_config* c) {
@@ -657,9 +667,16 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   A((void**)&s->selint, sizeof(int) * N);
   A((void**)&s->d_cnt2, sizeof(int) * 8);
   A((void**)&s->ctl, sizeof(EsikfCtl));
-  A((void**)&s->d_x0P0, sizeof(double) * (26 + NDOF * NDOF));
+  A((void**)&s->d_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
+  A((void**)&s->d_scr, sizeof(EsikfScratch));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ctl, sizeof(EsikfCtl));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&s->ev_fork[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess && cfg->max_iterations + 1 > 8) { flb_session_destroy(s); return set_err("max_iterations must be <= 7"); }
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_out, sizeof(double) * NACC);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_cnt2, sizeof(int) * 8);
   if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -690,12 +707,15 @@ extern "C" void flb_session_destroy(flb_session* s) {
   cudaSetDevice(s->map->cfg.device);
   cudaStreamSynchronize(s->map->stream);
   void* ptrs[] = {s->body, s->world, s->nbr, s->normvec, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
-                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->ctl, s->d_x0P0};
+                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->ctl, s->d_x0P0, s->d_scr};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->h_out) cudaFreeHost(s->h_out);
   if (s->h_cnt2) cudaFreeHost(s->h_cnt2);
   if (s->h_ctl) cudaFreeHost(s->h_ctl);
   if (s->h_x0P0) cudaFreeHost(s->h_x0P0);
+  for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+  for (int i = 0; i < 8; ++i) { if (s->ev_fork[i]) cudaEventDestroy(s->ev_fork[i]); if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]); }
+  if (s->side) cudaStreamDestroy(s->side);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev2) cudaEventDestroy(s->ev2);
@@ -769,7 +789,7 @@ static MeasArgs meas_args(flb_session* s, const PoseDev& pose, int search) {
   MeasArgs a;
   a.pose = pose; a.body = s->body; a.world = s->world; a.nbr = s->nbr; a.cnt = s->cnt; a.sel = s->sel;
   a.normvec = s->normvec; a.partial = s->partial; a.n = s->n; a.search = search;
-  a.ctl = nullptr; a.world_out = s->world;
+  a.ctl = nullptr; a.world_out = s->world; a.stride = s->cap;
   return a;
 }
 
@@ -790,7 +810,7 @@ static int enqueue_pass(flb_session* s, const double* state26, int search) {
     KnnArgs a;
     a.m = m->d; a.q = s->world; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
     a.phase_stats = m->prof_on ? m->d_phase : nullptr;
-    a.ctl = nullptr; a.body = nullptr;
+    a.ctl = nullptr; a.body = nullptr; a.stride = s->cap;
     if (launch_knn<5>(m, a)) return 1;
   }
   const MeasArgs ma = meas_args(s, pose, search);
@@ -923,45 +943,113 @@ static int run_update(flb_session* s, double* state26, double* P, flb_update_sta
 }
 
 
-// Device-driven update: every pass of the iterated update is enqueued up front (k-NN pair, residual, ESIKF step);
-// kernels of passes that turn out not to be needed exit on the device-side loop flags. No host round trip inside.
-static int enqueue_update_device(flb_session* s, const double* state26, const double* P) {
+static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl);
+
+// Device-driven scan: every pass of the iterated update (and optionally map_incremental) is enqueued up front; kernels
+// of passes that turn out not to be needed exit on the device-side loop flags.  No host round trip inside.  Launch
+// geometry depends only on the session capacity (the scan size n travels in the staging buffer), so the identical
+// sequence can be captured once into a CUDA graph.  k_esikf_pre of each pass runs on the side stream next to the
+// measurement kernels of that pass (fork/join by events, which become graph edges under capture).
+static int enqueue_scan_device(flb_session* s, bool with_insert) {
   flb_map* m = s->map;
   cudaStream_t st = m->stream;
-  const int n = s->n;
-  memcpy(s->h_x0P0, state26, sizeof(double) * 26);
-  memcpy(s->h_x0P0 + 26, P, sizeof(double) * NDOF * NDOF);
-  CU(cudaMemcpyAsync(s->d_x0P0, s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF), cudaMemcpyHostToDevice, st));
-  k_esikf_begin<<<1, 256, 0, st>>>(s->ctl, s->d_x0P0, s->d_x0P0 + 26, n);
+  const bool overlap = !m->prof_on;  // per-class event timing needs a single in-order stream
+  const int cap = s->cap;
+  CU(cudaMemcpyAsync(s->d_x0P0, s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2), cudaMemcpyHostToDevice, st));
+  k_esikf_begin<<<1, 256, 0, st>>>(s->ctl, s->d_x0P0);
   m->launches++;
   for (int p = 0; p <= s->cfg.max_iterations; ++p) {
-    if (n > 0) {
-      {
-        ProfScope ps(m, FLB_K_KNN);
-        KnnArgs a;
-        a.m = m->d; a.q = nullptr; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
-        a.phase_stats = m->prof_on ? m->d_phase : nullptr;
-        a.ctl = s->ctl; a.body = s->body;
-        if (launch_knn<5>(m, a)) return 1;
-      }
-      {
-        ProfScope ps(m, FLB_K_RESIDUAL);
-        MeasArgs ma = meas_args(s, PoseDev{}, 0);
-        ma.ctl = s->ctl;
-        if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
-        else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
-        m->launches++;
-      }
+    if (overlap) {
+      CU(cudaEventRecord(s->ev_fork[p], st));
+      CU(cudaStreamWaitEvent(s->side, s->ev_fork[p], 0));
+      k_esikf_pre<<<1, dev::ESIKF_THREADS, 0, s->side>>>(s->ctl, s->d_scr);
+      CU(cudaEventRecord(s->ev_join[p], s->side));
+    } else {
+      ProfScope ps(m, FLB_K_REDUCE);
+      k_esikf_pre<<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->d_scr);
+    }
+    m->launches++;
+    {
+      ProfScope ps(m, FLB_K_KNN);
+      KnnArgs a;
+      a.m = m->d; a.q = nullptr; a.n = cap; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
+      a.phase_stats = m->prof_on ? m->d_phase : nullptr;
+      a.ctl = s->ctl; a.body = s->body; a.stride = cap;
+      if (launch_knn<5>(m, a)) return 1;
     }
     {
+      ProfScope ps(m, FLB_K_RESIDUAL);
+      MeasArgs ma = meas_args(s, PoseDev{}, 0);
+      ma.ctl = s->ctl;
+      if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+      else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+      m->launches++;
+    }
+    if (overlap) CU(cudaStreamWaitEvent(st, s->ev_join[p], 0));
+    {
       ProfScope ps(m, FLB_K_REDUCE);
-      k_esikf_step<<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid);
+      k_esikf_post<<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid, s->d_scr);
       m->launches++;
     }
   }
   CU(cudaGetLastError());
+  if (with_insert && enqueue_map_incremental(s, nullptr, 0, true)) return 1;
   CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(EsikfCtl), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(m->h_counters, m->d.counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost, st));
   s->have_pass = false;
+  return 0;
+}
+
+// Stage a scan's inputs and run the device-driven sequence, through a CUDA graph when possible.
+static int launch_scan_device(flb_session* s, const double* state26, const double* P, int flg_EKF_inited, bool with_insert) {
+  flb_map* m = s->map;
+  memcpy(s->h_x0P0, state26, sizeof(double) * 26);
+  memcpy(s->h_x0P0 + 26, P, sizeof(double) * NDOF * NDOF);
+  s->h_x0P0[26 + NDOF * NDOF] = (double)s->n;
+  s->h_x0P0[26 + NDOF * NDOF + 1] = (double)flg_EKF_inited;
+  const int gi = with_insert ? 1 : 0;
+  if (!s->use_graph || m->prof_on) return enqueue_scan_device(s, with_insert);
+  if (!s->graph[gi]) {
+    // everything the captured sequence may allocate lazily must exist before capture
+    if (ensure_scratch(m, s->cap)) return 1;
+    if (s->cap > m->work_cap) {
+      if (m->worklist) cudaFree(m->worklist);
+      m->worklist = nullptr; m->work_cap = 0;
+      CU(cudaMalloc((void**)&m->worklist, sizeof(int) * (size_t)std::max(s->cap, 1 << 17)));
+      m->work_cap = std::max(s->cap, 1 << 17);
+    }
+    CU(cudaStreamSynchronize(m->stream));
+    const int l0 = m->launches;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+    m->capturing = true;
+    const int rc = enqueue_scan_device(s, with_insert);
+    m->capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(m->stream, &g);
+    if (rc || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      s->use_graph = false;  // fall back to direct launches (same kernels)
+      m->launches = l0;
+      return enqueue_scan_device(s, with_insert);
+    }
+    ce = cudaGraphInstantiate(&s->graph[gi], g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      s->graph[gi] = nullptr; s->use_graph = false; m->launches = l0;
+      return enqueue_scan_device(s, with_insert);
+    }
+    s->graph_kernels[gi] = m->launches - l0;
+    m->launches = l0;
+  }
+  CU(cudaGraphLaunch(s->graph[gi], m->stream));
+  m->launches += s->graph_kernels[gi];
+  return 0;
+}
+static int finish_counters(flb_map* m) {  // after the stream drained: interpret the counters copied by the sequence
+  const int e = m->h_counters[CNT_ERROR];
+  if (e) return set_err("device map error flags 0x%x (capacity exceeded or point out of range; see flb_map_get_stats)", e);
   return 0;
 }
 static void stats_from_ctl(const EsikfCtl* c, flb_update_stats* stats) {
@@ -976,9 +1064,10 @@ extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_
   if (!s->device_update) return run_update(s, state26, P, stats);
   flb_map* m = s->map;
   CU(cudaEventRecord(s->ev0, m->stream));
-  if (enqueue_update_device(s, state26, P)) return 1;
+  if (launch_scan_device(s, state26, P, 1, false)) return 1;
   CU(cudaEventRecord(s->ev1, m->stream));
   CU(cudaStreamSynchronize(m->stream));
+  if (finish_counters(m)) return 1;
   if (s->h_ctl->need_host) return run_update(s, state26, P, stats);  // M < 23: explicit-row branch on the host
   memcpy(state26, s->h_ctl->x, sizeof(double) * 26);
   memcpy(P, s->h_ctl->P, sizeof(double) * NDOF * NDOF);
@@ -987,21 +1076,23 @@ extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_
   return 0;
 }
 
-static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl = false) {
+static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl) {
   flb_map* m = s->map;
   cudaStream_t st = m->stream;
   const int n = s->n;
-  if (n <= 0) return 0;
+  if (n <= 0 && !from_ctl) return 0;
   const PoseDev pose = from_ctl ? PoseDev{} : pose_from(state26);
   CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
   {
     ProfScope ps(m, FLB_K_CLASSIFY);
-    k_classify<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, from_ctl ? s->ctl : nullptr, s->body, s->nbr, s->cnt, n,
+    k_classify<<<grid_for(from_ctl ? s->cap : n, 256, m->sm_count * 8), 256, 0, st>>>(pose, from_ctl ? s->ctl : nullptr, s->body, s->nbr, s->cnt, n, s->cap,
                                                                   flg_EKF_inited, s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
     m->launches++;
   }
   CU(cudaGetLastError());
-  if (insert_device(m, s->world, s->cls, n, 2, from_ctl ? &s->ctl->need_host : nullptr)) return 1;
+  if (from_ctl) {
+    if (insert_device(m, s->world, s->cls, s->cap, 2, &s->ctl->need_host, &s->ctl->n)) return 1;
+  } else if (insert_device(m, s->world, s->cls, n, 2)) return 1;
   CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   return 0;
 }
@@ -1012,7 +1103,7 @@ extern "C" int flb_map_incremental(flb_session* s, const double* state26, int fl
   if (n_to_add) *n_to_add = 0;
   if (n_no_ds) *n_no_ds = 0;
   if (s->n <= 0) return 0;
-  if (enqueue_map_incremental(s, state26, flg_EKF_inited)) return 1;
+  if (enqueue_map_incremental(s, state26, flg_EKF_inited, false)) return 1;
   if (fetch_counters(s->map)) return 1;
   if (n_to_add) *n_to_add = s->h_cnt2[0];
   if (n_no_ds) *n_no_ds = s->h_cnt2[1];
@@ -1029,14 +1120,14 @@ extern "C" int flb_neighbors_download(flb_session* s, float* nbr_xyz, float* nbr
   std::vector<float4> h4;
   std::vector<unsigned char> hc(n);
   if (nbr_xyz || nbr_d2) {
-    h4.resize((size_t)5 * n);
+    h4.resize((size_t)5 * s->cap);
     CU(cudaMemcpyAsync(h4.data(), s->nbr, sizeof(float4) * h4.size(), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hc.data(), s->cnt, n, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < 5; ++j) {
         const bool ok = j < hc[i];
-        const float4 v = h4[(size_t)j * n + i];
+        const float4 v = h4[(size_t)j * s->cap + i];
         if (nbr_xyz) { nbr_xyz[((size_t)i * 5 + j) * 3] = ok ? v.x : NAN; nbr_xyz[((size_t)i * 5 + j) * 3 + 1] = ok ? v.y : NAN; nbr_xyz[((size_t)i * 5 + j) * 3 + 2] = ok ? v.z : NAN; }
         if (nbr_d2) nbr_d2[(size_t)i * 5 + j] = ok ? v.w : INFINITY;
       }
@@ -1134,11 +1225,12 @@ extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* bo
     memcpy(prior_x, state26, sizeof(prior_x));
     memcpy(prior_P, P, sizeof(prior_P));
     CU(cudaEventRecord(s->ev0, m->stream));
-    if (enqueue_update_device(s, state26, P)) return 1;   // :2380, all passes enqueued without host round trips
+    if (launch_scan_device(s, state26, P, flg_EKF_inited, true)) return 1;  // :2380 + :2401, no host round trips inside
     CU(cudaEventRecord(s->ev1, m->stream));
-    if (s->n > 0 && enqueue_map_incremental(s, state26, flg_EKF_inited, true)) return 1;  // :2401 with the device posterior
     CU(cudaEventRecord(s->ev3, m->stream));
-    if (fetch_counters(m)) return 1;                       // the single synchronisation of the step
+    CU(cudaStreamSynchronize(m->stream));                  // the single synchronisation of the step
+    if (finish_counters(m)) return 1;
+    m->has_root = m->has_root || m->h_counters[CNT_VALID] > 0;
     if (s->h_ctl->need_host) {
       host_path = true;                                    // M < 23 branch: redo this scan on the host-driven path
       memcpy(state26, prior_x, sizeof(prior_x));
@@ -1152,7 +1244,7 @@ extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* bo
   }
   if (host_path) {
     if (run_update(s, state26, P, &r.update)) return 1;  // :2380
-    if (s->n > 0 && enqueue_map_incremental(s, state26, flg_EKF_inited)) return 1;  // :2401
+    if (s->n > 0 && enqueue_map_incremental(s, state26, flg_EKF_inited, false)) return 1;  // :2401
     CU(cudaEventRecord(s->ev3, m->stream));
     if (fetch_counters(m)) return 1;
   }

@@ -137,7 +137,8 @@ struct EsikfCtl {
   double last_res;
   PoseDev pose;        // pose of the current iterate
   int max_iter, it, t, converge, finished, need_host, passes, searches, lastM, n;
-  int pad_[2];
+  int flg_inited;      // flg_EKF_inited of this scan (laserMapping.cpp:2317)
+  int pad_;
 };
 __device__ __forceinline__ bool ctl_pass_active(const EsikfCtl* c) { return !c->finished && c->it < c->max_iter; }
 
@@ -153,6 +154,7 @@ struct KnnArgs {
   int* work_count;     // number of entries in worklist (device)
   const EsikfCtl* ctl; // device-driven mode: queries = body_to_world(ctl->pose, body[i]); skipped unless a search pass
   const float4* body;
+  int stride;          // leading dimension of nbr (>= n; the session capacity, so launches do not depend on n)
 };
 
 // visit every point of voxel slot `idx` (head + overflow chain)
@@ -181,7 +183,58 @@ __device__ __forceinline__ float cover2(float qx, float qy, float qz, float lx, 
   return c > 0.f ? c * c : 0.f;
 }
 
-// Process all blocks of one coarse cell (slot cs) with the whole warp: lane = block bit within each 32-bit half word.
+// Scan the blocks flagged in `todo` (one candidate block per lane: its index `myblk`, occupancy `mymask` and block
+// coordinates) with the WHOLE warp: two blocks per step, lane l reads slots l and l+32 of each, so the 4 point loads of
+// a step are issued back to back (memory-level parallelism) before the insertions.  Voxels inside the phase-A
+// stencil (|v - cv| <= 2) were already visited and are skipped when skip_stencil is set.
+template <int K>
+__device__ __forceinline__ void coop_scan_blocks(const MapDev& m, unsigned todo, int myblk, unsigned long long mymask, int mybx,
+                                                 int myby, int mybz, int lane, float qx, float qy, float qz, int cvx, int cvy,
+                                                 int cvz, bool skip_stencil, float limit, TopK<K>& t) {
+  while (todo) {
+    int src[2];
+    src[0] = __ffs(todo) - 1;
+    todo &= todo - 1;
+    src[1] = todo ? __ffs(todo) - 1 : -1;
+    if (src[1] >= 0) todo &= todo - 1;
+    float4 e[4];
+    bool v[4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int sl = src[u] >= 0 ? src[u] : 0;
+      const int blk = __shfl_sync(FULL, myblk, sl);
+      const unsigned long long mask = __shfl_sync(FULL, mymask, sl);
+      const int bx = __shfl_sync(FULL, mybx, sl), by = __shfl_sync(FULL, myby, sl), bz = __shfl_sync(FULL, mybz, sl);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int s = lane + 32 * h;
+        bool ok = src[u] >= 0 && ((mask >> s) & 1ull);
+        if (ok && skip_stencil) {
+          const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
+          ok = !(abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2);
+        }
+        v[u * 2 + h] = ok;
+        if (ok) e[u * 2 + h] = __ldg(&m.slots[(size_t)blk * 64 + s]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!v[j]) continue;
+      float4 p = e[j];
+      for (;;) {
+        const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
+        if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
+        const int c = __float_as_int(p.w);
+        if (c < 0) break;
+        p = __ldg(&m.ovf[c]);
+      }
+    }
+  }
+}
+
+// Process the blocks of one coarse cell (slot cs): per 32-bit group of the 512-bit block bitmap every lane tests its
+// block (bit set, not already covered by phase B0, box distance within the bound), probes the hash for it in
+// parallel, then the candidates are scanned co-operatively.
 template <int K>
 __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int lane, float qx, float qy, float qz,
                                                  int cvx, int cvy, int cvz, bool have, float thr, float lim, float mg,
@@ -191,6 +244,7 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
   unpack_key(__ldg(&m.ckeys[cs]), ccx, ccy, ccz);
   const float ds = m.ds;
   const float bs = 4.f * ds;
+  const float bound = have ? thr : CUDART_INF_F;
 #pragma unroll 1
   for (int k = 0; k < 8; ++k) {
     const unsigned long long word = __ldg(&m.cbits[(size_t)cs * 8 + k]);
@@ -198,21 +252,22 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int bit = k * 64 + h * 32 + lane;
-      if (!((word >> (h * 32 + lane)) & 1ull)) continue;
       const int bx = ccx * 8 + (bit & 7), by = ccy * 8 + ((bit >> 3) & 7), bz = ccz * 8 + (bit >> 6);
-      if (abs(bx - qbx_) <= 1 && abs(by - qby_) <= 1 && abs(bz - qbz_) <= 1) continue;  // visited by phase B0
-      const float lx = (float)bx * bs, ly = (float)by * bs, lz = (float)bz * bs;
-      const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs, ly + bs, lz + bs, mg);
-      const float bound = (have || t.d[K - 1] < CUDART_INF_F) ? fminf(thr, t.d[K - 1]) : CUDART_INF_F;
-      if (md > bound || md > lim) continue;
-      const int blk = find_block(m, pack_key(bx, by, bz));
-      if (blk < 0) continue;
-      unsigned long long mask = __ldg(&m.bmask[blk]);
-      while (mask) {
-        const int s = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, fminf(lim, bound), t);
+      bool go = (word >> (h * 32 + lane)) & 1ull;
+      if (go && abs(bx - qbx_) <= 1 && abs(by - qby_) <= 1 && abs(bz - qbz_) <= 1) go = false;  // visited by phase B0
+      if (go) {
+        const float lx = (float)bx * bs, ly = (float)by * bs, lz = (float)bz * bs;
+        const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs, ly + bs, lz + bs, mg);
+        go = !(md > bound || md > lim);
       }
+      int blk = -1;
+      unsigned long long mask = 0ull;
+      if (go) {
+        blk = find_block(m, pack_key(bx, by, bz));
+        if (blk >= 0) mask = __ldg(&m.bmask[blk]);
+      }
+      const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
+      if (todo) coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, false, fminf(lim, bound), t);
     }
   }
 }
@@ -269,19 +324,16 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
         // ---------------- phase B0: the 3x3x3 BLOCKS around the query block (one block per lane): covers >= 4 voxels
         // around the query, enough for almost every query the stencil could not settle, and gives phase B a finite bound
         phase = 1;
-        if (lane < 27) {
-          const int bx = qbx + (lane % 3) - 1, by = qby + ((lane / 3) % 3) - 1, bz = qbz + (lane / 9) - 1;
-          const int blk = find_block(m, pack_key(bx, by, bz));
-          if (blk >= 0) {
-            unsigned long long mask = __ldg(&m.bmask[blk]);
-            while (mask) {
-              const int s = __ffsll((long long)mask) - 1;
-              mask &= mask - 1;
-              const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
-              if (abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2) continue;  // stencil: done in A
-              visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, fminf(lim, fminf(thr, t.d[K - 1])), t);
-            }
+        {
+          int bx = 0, by = 0, bz = 0, blk = -1;
+          unsigned long long mask = 0ull;
+          if (lane < 27) {
+            bx = qbx + (lane % 3) - 1; by = qby + ((lane / 3) % 3) - 1; bz = qbz + (lane / 9) - 1;
+            blk = find_block(m, pack_key(bx, by, bz));
+            if (blk >= 0) mask = __ldg(&m.bmask[blk]);
           }
+          const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
+          coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, true, fminf(lim, thr), t);
         }
         gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
         const float bs4 = 4.f * ds;
@@ -300,6 +352,7 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
         {
           const int cs = __shfl_sync(FULL, mycs, 13);
           if (cs >= 0) scan_coarse_cell<K>(m, cs, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
+          if (gcount < K) gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);  // get a finite bound before the ring
         }
         unsigned rest = present & ~(1u << 13);
         while (rest) {
@@ -343,7 +396,7 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
         }
       }
     }
-    if (lane < K) a.nbr[(size_t)lane * a.n + i] = make_float4(rx, ry, rz, rd);
+    if (lane < K) a.nbr[(size_t)lane * a.stride + i] = make_float4(rx, ry, rz, rd);
     if (lane == 0) {
       a.cnt[i] = (unsigned char)gcount;
       if (a.phase_stats) atomicAdd(&a.phase_stats[phase], 1);
@@ -392,8 +445,8 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
   const MapDev& m = a.m;
   const int tid = threadIdx.x;
   const int i = blockIdx.x * blockDim.x + tid;
-  if (i >= a.n) return;
   if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
+  if (i >= (a.ctl ? a.ctl->n : a.n)) return;
   const float ds = m.ds;
   const float lim = a.max_d2;
   const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
@@ -464,7 +517,7 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
         const float4 e = (t.id[r] & 0x80000000u) ? __ldg(&m.ovf[t.id[r] & 0x7FFFFFFFu]) : __ldg(&m.slots[t.id[r]]);
         o = make_float4(e.x, e.y, e.z, t.d[r]);
       }
-      a.nbr[(size_t)r * a.n + i] = o;
+      a.nbr[(size_t)r * a.stride + i] = o;
     }
     a.cnt[i] = (unsigned char)c;
     if (a.phase_stats) atomicAdd(&a.phase_stats[0], 1);

@@ -115,8 +115,9 @@ __device__ __forceinline__ void touch_block(const MapDev& m, uint64_t key, int b
 // ---------------------------------------------------------------------------------------------- K3a: touch blocks
 // cls == nullptr: every point; else only points whose class has its bit in cls_mask (bit1: ToAdd, bit2: NoNeed).
 __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
-                               int cls_mask, int n, const int* __restrict__ skip) {
+                               int cls_mask, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
   if (skip && *skip) return;
+  if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (cls && !((1 << cls[i]) & cls_mask)) continue;
     const float4 p = pts[i];
@@ -129,8 +130,9 @@ __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const u
 // ---------------------------------------------------------------------------------------------- K3b: verbatim append
 // Add_Points(..., downsample_on=false) (ikd_Tree.cpp:471-472) and Build (ikd_Tree.cpp:352-364): no dedupe.
 __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
-                                int want_cls, int n, const int* __restrict__ skip) {
+                                int want_cls, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
   if (skip && *skip) return;
+  if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (cls && cls[i] != want_cls) continue;
     const float4 p = pts[i];
@@ -183,8 +185,10 @@ __device__ __forceinline__ float dist_pt_to_centre_of(const float4 e, const floa
 // Scratch hash: per voxel touched by this batch, the best NEW point = min (dist to centre, later index wins ties —
 // the reference processes points in order and a later point replaces an equal-distance earlier one, :436-447).
 __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int n,
-                             uint64_t* skeys, unsigned long long* sbest, uint32_t smask, const int* __restrict__ skip) {
+                             uint64_t* skeys, unsigned long long* sbest, uint32_t smask, const int* __restrict__ skip,
+                             const int* __restrict__ n_dev) {
   if (skip && *skip) return;
+  if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (cls && cls[i] != 1) continue;
     const float4 p = pts[i];
@@ -212,8 +216,9 @@ __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const uns
 // disagree with that within 1 ulp of a voxel face (documented deviation).
 __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int n,
                            const uint64_t* __restrict__ skeys, const unsigned long long* __restrict__ sbest,
-                           uint32_t smask, const int* __restrict__ skip) {
+                           uint32_t smask, const int* __restrict__ skip, const int* __restrict__ n_dev) {
   if (skip && *skip) return;
+  if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (cls && cls[i] != 1) continue;
     const float4 p = pts[i];

@@ -178,6 +178,7 @@ struct MeasArgs {
   int search;                 // ekfom_data.converge
   const EsikfCtl* ctl;        // device-driven mode: pose / search flag / early exit come from here
   float4* world_out;          // device-driven mode: feats_down_world is produced here (no separate K0)
+  int stride;                 // leading dimension of nbr
 };
 
 __constant__ unsigned char c_tri_i[91];
@@ -219,7 +220,7 @@ __device__ __forceinline__ bool select_point(const MeasArgs& a, int i, int searc
   bool sel;
   if (search) {
     const int c = a.cnt[i];
-    const float d4 = a.nbr[(size_t)4 * a.n + i].w;
+    const float d4 = a.nbr[(size_t)4 * a.stride + i].w;
     sel = (c < 5) ? false : (d4 > 5.f ? false : true);        // :1911
   } else {
     sel = a.sel[i] != 0;
@@ -228,7 +229,7 @@ __device__ __forceinline__ bool select_point(const MeasArgs& a, int i, int searc
   float P[5][3];
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const float4 q = a.nbr[(size_t)j * a.n + i];
+    const float4 q = a.nbr[(size_t)j * a.stride + i];
     P[j][0] = q.x; P[j][1] = q.y; P[j][2] = q.z;
   }
   float pa, pb_, pc, pd;
@@ -258,13 +259,14 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
   if (a.ctl && !ctl_pass_active(a.ctl)) return;   // the iterated update already finished (block-uniform)
   const PoseDev pose = a.ctl ? a.ctl->pose : a.pose;
   const int search = a.ctl ? a.ctl->converge : a.search;
+  const int n = a.ctl ? a.ctl->n : a.n;
   const int stride = gridDim.x * blockDim.x;
-  const int nround = (a.n + stride - 1) / stride;
+  const int nround = (n + stride - 1) / stride;
   for (int it = 0; it < nround; ++it) {
     const int i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
     float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
     bool sel = false;
-    if (i < a.n) {
+    if (i < n) {
       float4 pw;
       if (a.ctl) { pw = body_to_world(pose, a.body[i]); a.world_out[i] = pw; }
       else pw = a.world[i];
@@ -373,10 +375,12 @@ __global__ void k_sel_to_int(const unsigned char* __restrict__ sel, int* __restr
 // laserMapping.cpp:1440-1490. cls: 0 dropped, 1 PointToAdd (downsample), 2 PointNoNeedDownsample.
 // counts[0] += #ToAdd, counts[1] += #NoNeed.
 __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __restrict__ body, const float4* __restrict__ nbr,
-                           const unsigned char* __restrict__ cnt, int n, int flg_EKF_inited, double fs,
+                           const unsigned char* __restrict__ cnt, int n_in, int nbr_stride, int flg_in, double fs,
                            float4* __restrict__ world, unsigned char* __restrict__ cls, int* counts) {
   if (ctl && ctl->need_host) return;  // the host fallback redoes update + insert for this scan
   const PoseDev s = ctl ? ctl->pose : s_in;
+  const int n = ctl ? ctl->n : n_in;
+  const int flg_EKF_inited = ctl ? ctl->flg_inited : flg_in;
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * blockDim.x;
   const int nround = (n + stride - 1) / stride;
@@ -401,7 +405,7 @@ __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __re
           if (k >= 5) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-              const float4 q = nbr[(size_t)j * n + i];
+              const float4 q = nbr[(size_t)j * nbr_stride + i];
               if (sqdist(q.x, q.y, q.z, hf_x, hf_y, hf_z) < dist) { need_add = false; break; }
             }
           }

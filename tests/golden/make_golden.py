@@ -46,7 +46,7 @@ def make(name, seed, model, ext, map_half, stride):
     np.savez_compressed(out, map=mp, body=body, prior=prior, P=P, ext=np.array(ext), nn_d2=d0, nn_cnt=c0, sel0=sel,
                         M0=np.array(M0), HTH0=hx0.T @ hx0, HTh0=hx0.T @ h0, tot0=np.array(tot0), post=st, P_post=Pp,
                         stats=stats, trace=trace, cls=cls, final_count=np.array(len(final)),
-                        final_sha256=np.array(digest(final)), truth=st_true)
+                        final_sha256=np.array(digest(final)), final_sorted=final, truth=st_true)
     print(name, "map", mp.shape, "body", body.shape, "M0", M0, "stats", stats, "final", len(final),
           os.path.getsize(out) // 1024, "KiB")
 

@@ -38,3 +38,27 @@ def knn_equal(d2_a, xyz_a, cnt_a, d2_b, xyz_b, cnt_b):
     xb = np.where(np.isfinite(xyz_b[ok]), xyz_b[ok], 0)
     assert np.array_equal(xa, xb)
     return int(tie.sum())
+
+
+def maps_match(a, b, tol=2e-6):
+    """Same point set up to float rounding of individual coordinates: the inserted world points are float roundings
+    of a double transform, so two engines whose states agree to ~1e-13 can differ by 1 ulp in a few coordinates."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    if len(a) != len(b):
+        return False, f"sizes {len(a)} != {len(b)}"
+    va = a.view([("", a.dtype)] * 3).ravel()
+    vb = b.view([("", b.dtype)] * 3).ravel()
+    only_a = a[~np.isin(va, vb)]
+    only_b = b[~np.isin(vb, va)]
+    if len(only_a) != len(only_b):
+        return False, f"unmatched {len(only_a)} vs {len(only_b)}"
+    if len(only_a) > max(20, len(a) // 1000):
+        return False, f"too many rounding differences: {len(only_a)}"
+    for p in only_a:
+        d = np.abs(only_b - p).max(1)
+        j = int(np.argmin(d))
+        if d[j] > tol * max(1.0, float(np.abs(p).max())):
+            return False, f"point {p} has no partner within tolerance (best {d[j]})"
+        only_b = np.delete(only_b, j, 0)
+    return True, f"{len(only_a)} coordinates differ by rounding"
