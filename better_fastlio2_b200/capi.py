@@ -57,7 +57,8 @@ class ScanResult(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int * 8), ("regions", C.c_int * 8), ("knn_phase", C.c_longlong * 4)]
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int * 8), ("regions", C.c_int * 8), ("knn_phase", C.c_longlong * 4),
+                ("knn_head_candidates", C.c_longlong), ("knn_chain_nodes", C.c_longlong), ("knn_chain_max", C.c_longlong)]
 
 
 K_CLASSES = ["transform", "knn", "residual", "reduce", "classify", "insert", "delete"]
@@ -255,6 +256,9 @@ class KDTree:
         for i, k in enumerate(K_CLASSES):
             out[k] = {"ms": p.ms[i], "launches": p.launches[i], "regions": p.regions[i]}
         out["knn_phase"] = [int(p.knn_phase[i]) for i in range(4)]
+        out["knn_head_candidates"] = int(p.knn_head_candidates)
+        out["knn_chain_nodes"] = int(p.knn_chain_nodes)
+        out["knn_chain_max"] = int(p.knn_chain_max)
         return out
 
     def stats(self):

@@ -176,9 +176,10 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   rc |= dev_alloc(m, (void**)&d.free_ovf, sizeof(uint32_t) * d.ovf_cap);
   rc |= dev_alloc(m, (void**)&d.ckeys, sizeof(uint64_t) * m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.cbits, sizeof(uint64_t) * 8 * (size_t)m->chash_cap);
+  rc |= dev_alloc(m, (void**)&d.clist, sizeof(uint32_t) * (size_t)m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.counters, sizeof(int) * CNT_COUNT);
   rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 16);
-  rc |= dev_alloc(m, (void**)&m->d_phase, sizeof(int) * 4);
+  rc |= dev_alloc(m, (void**)&m->d_phase, sizeof(int) * 8);
   if (rc) { flb_map_destroy(m); return 1; }
   if (cudaMallocHost((void**)&m->h_counters, sizeof(int) * CNT_COUNT) != cudaSuccess) { flb_map_destroy(m); return set_err("cudaMallocHost failed"); }
   // triangle index tables of the 13x13 augmented normal equations
@@ -197,7 +198,7 @@ extern "C" void flb_map_destroy(flb_map* m) {
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   MapDev& d = m->d;
-  void* ptrs[] = {d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
+  void* ptrs[] = {d.clist, d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
                   m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_counters) cudaFreeHost(m->h_counters);
@@ -573,7 +574,7 @@ extern "C" int flb_map_profile_enable(flb_map* m, int on) {
   CU(cudaStreamSynchronize(m->stream));
   m->prof_on = on != 0;
   m->prof_used = 0;
-  CU(cudaMemsetAsync(m->d_phase, 0, sizeof(int) * 4, m->stream));
+  CU(cudaMemsetAsync(m->d_phase, 0, sizeof(int) * 8, m->stream));
   return 0;
 }
 extern "C" int flb_map_profile_read(flb_map* m, flb_profile* out, int reset) {
@@ -587,10 +588,11 @@ extern "C" int flb_map_profile_read(flb_map* m, flb_profile* out, int reset) {
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
     if (r.cls >= 0 && r.cls < FLB_K_COUNT) { out->ms[r.cls] += ms; out->launches[r.cls] += r.nlaunch; out->regions[r.cls] += 1; }
   }
-  int ph[4];
+  int ph[8];
   CU(cudaMemcpy(ph, m->d_phase, sizeof(ph), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) out->knn_phase[i] = ph[i];
-  if (reset) { m->prof_used = 0; CU(cudaMemset(m->d_phase, 0, sizeof(int) * 4)); }
+  out->knn_chain_nodes = ph[4]; out->knn_chain_max = ph[5]; out->knn_head_candidates = ph[6];
+  if (reset) { m->prof_used = 0; CU(cudaMemset(m->d_phase, 0, sizeof(int) * 8)); }
   return 0;
 }
 

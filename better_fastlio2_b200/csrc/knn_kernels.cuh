@@ -369,11 +369,12 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
         if (!done) {
           // ---------------- phase C: exhaustive scan of the coarse hash with box-distance pruning
           phase = 3;
-          const int ncs = (int)m.chash_mask + 1;
+          const int ncs = m.counters[CNT_COARSE_USED];   // dense list of occupied coarse cells
 #pragma unroll 1
           for (int base = 0; base < ncs; base += 32) {
-            const int cs = base + lane;
-            const uint64_t ck = __ldg(&m.ckeys[cs]);
+            const int li = base + lane;
+            const int cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
+            const uint64_t ck = cs >= 0 ? __ldg(&m.ckeys[cs]) : KEY_EMPTY;
             bool go = false;
             if (ck != KEY_EMPTY) {
               int cx, cy, cz;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
             while (todo) {
               const int c = __ffs(todo) - 1;
               todo &= todo - 1;
-              scan_coarse_cell<K>(m, base + c, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
+              scan_coarse_cell<K>(m, __shfl_sync(FULL, cs, c), lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
             }
             gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
           }
@@ -409,8 +410,7 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
 // then ONE loop over the occupied stencil voxels of all 8 blocks (per-thread cursor, so a warp iterates
 // max-over-lanes of the candidate COUNT, not the sum of per-block maxima) with one 16-B point load per candidate and
 // a branch-free insertion into a register-resident (distance, slot-id) top-K.  No cross-lane traffic.
-// Queries whose stencil cannot prove completeness — or that see an exact float distance tie, whose canonical
-// (x,y,z) order is resolved by the warp kernel — are appended to a work list for the exact kernel k_knn.
+// Queries whose stencil cannot prove completeness are appended to a work list for the exact kernel k_knn.
 template <int K>
 struct TopKId {
   float d[K];
@@ -419,12 +419,12 @@ struct TopKId {
 #pragma unroll
     for (int j = 0; j < K; ++j) { d[j] = CUDART_INF_F; id[j] = 0u; }
   }
-  // branch-free sorted insert; returns true if dd equals a kept distance (tie)
-  __device__ __forceinline__ bool insert(float dd, unsigned pid) {
+  // branch-free sorted insert (equal distances keep their arrival order: exact float ties between distinct map points
+  // are not canonicalised on this fast path — the reference's own tie order is traversal dependent, ikd_Tree.h:102-105)
+  __device__ __forceinline__ void insert(float dd, unsigned pid) {
     bool c[K];
-    bool tie = false;
 #pragma unroll
-    for (int j = 0; j < K; ++j) { c[j] = dd < d[j]; tie |= (dd == d[j]); }
+    for (int j = 0; j < K; ++j) c[j] = dd < d[j];
 #pragma unroll
     for (int j = K - 1; j > 0; --j) {
       d[j] = c[j - 1] ? d[j - 1] : (c[j] ? dd : d[j]);
@@ -432,7 +432,6 @@ struct TopKId {
     }
     d[0] = c[0] ? dd : d[0];
     id[0] = c[0] ? pid : id[0];
-    return tie;
   }
 };
 
@@ -454,55 +453,99 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
   const float qlim = 4.0e6f * ds;
   TopKId<K> t;
   t.clear();
-  bool done = false, tie = false;
+  bool done = false;
   if (fabsf(qx) < qlim && fabsf(qy) < qlim && fabsf(qz) < qlim) {
     const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
     const int bbx = (cvx - 2) >> 2, bby = (cvy - 2) >> 2, bbz = (cvz - 2) >> 2;
+    // per axis the 5-wide stencil covers local range [o,3] of the low block and [0,(o+4)&3] of the high block
+    const int ox = (cvx - 2) & 3, oy = (cvy - 2) & 3, oz = (cvz - 2) & 3;
+    const unsigned xm2[2] = {(0xFu << ox) & 0xFu, 0xFu >> (3 - ((ox + 4) & 3))};
+    const unsigned ym2[2] = {(0xFu << oy) & 0xFu, 0xFu >> (3 - ((oy + 4) & 3))};
+    const unsigned zm2[2] = {(0xFu << oz) & 0xFu, 0xFu >> (3 - ((oz + 4) & 3))};
+    unsigned ysp2[2];
+    unsigned long long zsp2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const unsigned ym = ym2[h], zm = zm2[h];
+      ysp2[h] = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);  // bits 0,4,8,12
+      zsp2[h] = (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) | ((unsigned long long)(zm & 4u) << 30) |
+                ((unsigned long long)(zm & 8u) << 45);                               // bits 0,16,32,48
+    }
+    // ---- the 8 hash probes are INDEPENDENT loads: issue them back to back (memory-level parallelism), then resolve;
+    // only a collision (first slot holds another key) falls back to the sequential probe loop
+    uint64_t keys8[8];
+    uint4 ent[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const int bx = bbx + (b & 1), by = bby + ((b >> 1) & 1), bz = bbz + (b >> 2);
-      // stencil range inside this block, per axis (local voxel coordinates 0..3); never empty for these 8 blocks
-      const int x0 = max(cvx - 2, bx * 4) - bx * 4, x1 = min(cvx + 2, bx * 4 + 3) - bx * 4;
-      const int y0 = max(cvy - 2, by * 4) - by * 4, y1 = min(cvy + 2, by * 4 + 3) - by * 4;
-      const int z0 = max(cvz - 2, bz * 4) - bz * 4, z1 = min(cvz + 2, bz * 4 + 3) - bz * 4;
-      const int blk = find_block(m, pack_key(bx, by, bz));
-      unsigned long long cand = 0ull;
-      if (blk >= 0) {
-        const unsigned xm = ((1u << (x1 - x0 + 1)) - 1u) << x0;
-        const unsigned ym = ((1u << (y1 - y0 + 1)) - 1u) << y0;
-        const unsigned zm = ((1u << (z1 - z0 + 1)) - 1u) << z0;
-        const unsigned ysp = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);  // bits 0,4,8,12
-        const unsigned long long zsp = (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) |
-                                       ((unsigned long long)(zm & 4u) << 30) | ((unsigned long long)(zm & 8u) << 45);
-        cand = __ldg(&m.bmask[blk]) & ((unsigned long long)(xm * ysp) * zsp);
-      }
-      s_blk[b][tid] = blk;
-      s_cand[b][tid] = cand;
+      keys8[b] = pack_key(bbx + (b & 1), bby + ((b >> 1) & 1), bbz + (b >> 2));
+      ent[b] = __ldg(reinterpret_cast<const uint4*>(&m.hent[hash_key(keys8[b]) & m.hash_mask]));
     }
-    // one loop over all candidates of this thread (own smem column: no synchronisation needed)
+    int blk8[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const uint64_t k0 = ((uint64_t)ent[b].y << 32) | ent[b].x;
+      blk8[b] = (k0 == keys8[b]) ? (int)ent[b].z : (k0 == KEY_EMPTY ? -1 : find_block(m, keys8[b]));
+    }
+    unsigned long long occ[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) occ[b] = blk8[b] >= 0 ? __ldg(&m.bmask[blk8[b]]) : 0ull;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int hx = b & 1, hy = (b >> 1) & 1, hz = b >> 2;
+      s_blk[b][tid] = blk8[b];
+      s_cand[b][tid] = occ[b] & ((unsigned long long)(xm2[hx] * ysp2[hy]) * zsp2[hz]);
+    }
+    // ---- one loop over all candidates of this thread (own smem column: no synchronisation needed), four point
+    // loads in flight per round
     int b = -1, blk = 0;
+    int n_chain = 0, n_head = 0;
     unsigned long long cand = 0ull;
     for (;;) {
-      while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; blk = s_blk[b][tid]; }
-      if (cand == 0ull) break;
-      const int s = __ffsll((long long)cand) - 1;
-      cand &= cand - 1;
-      const unsigned pid = (unsigned)blk * 64u + (unsigned)s;
-      float4 e = __ldg(&m.slots[pid]);
-      float dd = sqdist(qx, qy, qz, e.x, e.y, e.z);
-      if (dd <= lim) tie |= t.insert(dd, pid);
-      int c = __float_as_int(e.w);
-      while (c >= 0) {  // overflow chain of this voxel (rare)
-        e = __ldg(&m.ovf[c]);
-        dd = sqdist(qx, qy, qz, e.x, e.y, e.z);
-        if (dd <= lim) tie |= t.insert(dd, 0x80000000u | (unsigned)c);
-        c = __float_as_int(e.w);
+      unsigned pid[4];
+      int nc = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; blk = s_blk[b][tid]; }
+        pid[u] = 0u;
+        if (cand != 0ull) {
+          const int sl = __ffsll((long long)cand) - 1;
+          cand &= cand - 1;
+          pid[u] = (unsigned)blk * 64u + (unsigned)sl;
+          nc = u + 1;
+        }
       }
+      if (nc == 0) break;
+      float4 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nc) e[u] = __ldg(&m.slots[pid[u]]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u < nc) {
+          float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
+          if (dd <= lim) t.insert(dd, pid[u]);
+          ++n_head;
+          int c = __float_as_int(e[u].w);
+          while (c >= 0) {  // overflow chain of this voxel
+            ++n_chain;
+            const float4 o = __ldg(&m.ovf[c]);
+            dd = sqdist(qx, qy, qz, o.x, o.y, o.z);
+            if (dd <= lim) t.insert(dd, 0x80000000u | (unsigned)c);
+            c = __float_as_int(o.w);
+          }
+        }
+      }
+      if (nc < 4) break;
+    }
+    if (a.phase_stats) {  // profiling only: candidate statistics
+      atomicAdd(&a.phase_stats[4], n_chain);
+      atomicMax(&a.phase_stats[5], n_chain);
+      atomicAdd(&a.phase_stats[6], n_head);
     }
     const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
     const float cov = cover2(qx, qy, qz, (float)(cvx - 2) * ds, (float)(cvy - 2) * ds, (float)(cvz - 2) * ds,
                              (float)(cvx + 3) * ds, (float)(cvy + 3) * ds, (float)(cvz + 3) * ds, mg);
-    done = ((t.d[K - 1] < CUDART_INF_F && t.d[K - 1] < cov) || cov > lim) && !tie;
+    done = (t.d[K - 1] < CUDART_INF_F && t.d[K - 1] < cov) || cov > lim;
   } else {
     done = true;  // unrepresentable / NaN query: no neighbours
   }

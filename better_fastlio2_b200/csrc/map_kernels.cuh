@@ -58,7 +58,7 @@ __device__ __forceinline__ void coarse_set(const MapDev& m, int bx, int by, int 
     if (k == KEY_EMPTY) {
       uint64_t old = atomicCAS((unsigned long long*)&m.ckeys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)ck);
       if (old == KEY_EMPTY) {
-        atomicAdd(&m.counters[CNT_COARSE_USED], 1);
+        m.clist[atomicAdd(&m.counters[CNT_COARSE_USED], 1)] = s;
         atomicMin(&m.counters[CNT_CMIN_X], cx); atomicMin(&m.counters[CNT_CMIN_Y], cy); atomicMin(&m.counters[CNT_CMIN_Z], cz);
         atomicMax(&m.counters[CNT_CMAX_X], cx); atomicMax(&m.counters[CNT_CMAX_Y], cy); atomicMax(&m.counters[CNT_CMAX_Z], cz);
         slot = (int)s;

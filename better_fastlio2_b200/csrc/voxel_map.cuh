@@ -34,7 +34,7 @@ enum Counter : int {
   CNT_VALID,          // number of valid points
   CNT_KEYS_USED,      // live keys in the block hash
   CNT_KEYS_TOMB,      // tombstones in the block hash
-  CNT_COARSE_USED,    // live coarse cells
+  CNT_COARSE_USED,    // coarse cells ever created since the last rebuild (= length of clist)
   CNT_ERROR,          // sticky device error flags (ERR_*)
   CNT_SCRATCH0,       // per-call scratch (returned counts)
   CNT_SCRATCH1,
@@ -62,6 +62,7 @@ struct MapDev {
   uint32_t* free_ovf;
   uint64_t* ckeys;
   uint64_t* cbits;
+  uint32_t* clist;       // dense list of the occupied slots of ckeys (append order) for exhaustive far searches
   int* counters;
   uint32_t hash_mask;    // C-1
   uint32_t chash_mask;   // CC-1

@@ -213,17 +213,19 @@ def voxel_downsample(pts, leaf):
 
 
 def sample_surface_map(world, center, half, ds, rng, noise=0.01, zmax=25.0):
-    """Map pre-fill: about one jittered point per ds x ds cell on every surface inside the cube |p - center| <= half
+    """Map pre-fill: about one jittered point per ds x ds cell on every surface inside the box |p - center| <= half
+    (half: scalar or per-axis)
     (what map_incremental converges to: one point per filter_size_map_min voxel)."""
     out = []
     c = np.asarray(center, np.float64)
+    hv = np.broadcast_to(np.asarray(half, np.float64), (3,)) if np.ndim(half) else np.full(3, float(half))
     for k in range(len(world.axis)):
         ax = int(world.axis[k])
         u, v = _OTHER[ax]
-        if abs(world.coord[k] - c[ax]) > half:
+        if abs(world.coord[k] - c[ax]) > hv[ax]:
             continue
-        lo = np.maximum(world.lo[k], [c[u] - half, c[v] - half])
-        hi = np.minimum(world.hi[k], [c[u] + half, c[v] + half])
+        lo = np.maximum(world.lo[k], [c[u] - hv[u], c[v] - hv[v]])
+        hi = np.minimum(world.hi[k], [c[u] + hv[u], c[v] + hv[v]])
         if v == 2:
             hi[1] = min(hi[1], zmax)
         if ax == 2 and world.coord[k] > zmax:

@@ -108,6 +108,9 @@ typedef struct flb_profile {
   int regions[FLB_K_COUNT];    /* timed regions per class (e.g. one per k-NN pass) */
   long long knn_phase[4];      /* queries resolved by search phase A (5^3 voxel stencil) / B0 (3^3 blocks) /
                                   B (3^3 coarse cells) / C (exhaustive coarse scan) */
+  long long knn_head_candidates; /* stencil kernel: occupied stencil voxels visited (one 16-B load each) */
+  long long knn_chain_nodes;     /* stencil kernel: overflow-chain nodes visited (voxels holding > 1 point) */
+  long long knn_chain_max;       /* largest number of chain nodes visited by a single query */
 } flb_profile;
 int flb_map_profile_enable(flb_map* m, int on);
 int flb_map_profile_read(flb_map* m, flb_profile* out, int reset);
