@@ -73,6 +73,26 @@ void ikdref_nearest(void* h, const float* q, int nq, int k, float* out_xyz, floa
   }
 }
 
+// same with the reference's max_dist argument (ikd_Tree.h:236, candidates with dist > max_dist^2 are not accepted)
+void ikdref_nearest_md(void* h, const float* q, int nq, int k, double max_dist, float* out_xyz, float* out_d2, int* out_cnt) {
+  Tree* t = static_cast<Tree*>(h);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < nq; i++) {
+    PV nn;
+    std::vector<float> d2;
+    t->Nearest_Search(mk(q + 3 * i), k, nn, d2, max_dist);
+    int c = (int)nn.size();
+    out_cnt[i] = c;
+    for (int j = 0; j < k; j++) {
+      const size_t o = (size_t)i * k + j;
+      out_xyz[3 * o] = j < c ? nn[j].x : NAN;
+      out_xyz[3 * o + 1] = j < c ? nn[j].y : NAN;
+      out_xyz[3 * o + 2] = j < c ? nn[j].z : NAN;
+      out_d2[o] = j < c ? d2[j] : INFINITY;
+    }
+  }
+}
+
 // orc_knn5_fn-compatible adapter (see lio_oracle.cpp): 5-NN with the thread count set by ikdref_set_threads.
 static int g_knn_threads = 0;
 void ikdref_set_threads(int t) { g_knn_threads = t; }

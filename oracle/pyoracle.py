@@ -82,6 +82,8 @@ def ref():
         L.ikdref_set_threads.argtypes = [C.c_int]
         L.ikdref_has_root.argtypes = [C.c_void_p]
         L.ikdref_has_root.restype = C.c_int
+        L.ikdref_nearest_md.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_double, f32p, f32p, i32p]
+        L.ikdref_delete_points.argtypes = [C.c_void_p, f32p, C.c_int]
         _ref = L
     return _ref
 
@@ -190,6 +192,19 @@ class RefIkdTree(_MapBase):
 
     def set_threads(self, t):
         self._L.ikdref_set_threads(int(t))
+
+    def Nearest_Search_md(self, q, k, max_dist):
+        q = _xyz(q)
+        n = len(q)
+        xyz = np.empty((n, k, 3), np.float32)
+        d2 = np.empty((n, k), np.float32)
+        cnt = np.empty(n, np.int32)
+        self._L.ikdref_nearest_md(self.h, q, n, k, float(max_dist), xyz.reshape(-1), d2.reshape(-1), cnt)
+        return xyz, d2, cnt
+
+    def Delete_Points(self, pts):
+        pts = _xyz(pts)
+        self._L.ikdref_delete_points(self.h, pts, len(pts))
 
 
 class PortMap(_MapBase):
