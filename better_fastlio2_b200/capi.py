@@ -74,7 +74,7 @@ EXPORTS = [
     "flb_map_get_stats", "flb_session_default_config", "flb_session_create", "flb_session_destroy", "flb_scan_upload",
     "flb_scan_set_device", "flb_pass", "flb_pass_rows", "flb_esikf_update", "flb_map_incremental",
     "flb_neighbors_download", "flb_fov_segment", "flb_scan_step", "flb_session_stream", "flb_session_sync",
-    "flb_map_profile_enable", "flb_map_profile_read", "flb_session_set_update_engine",
+    "flb_map_profile_enable", "flb_map_profile_read", "flb_session_set_update_engine", "flb_scan_prefetch", "flb_scan_step_begin", "flb_scan_step_finish",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
         L.flb_session_destroy.restype = None
         L.flb_scan_upload.argtypes = [vp, fp, C.c_int, C.c_int]
         L.flb_scan_set_device.argtypes = [vp, vp, C.c_int]
+        L.flb_scan_prefetch.argtypes = [vp, fp, C.c_int, C.c_int]
         L.flb_pass.argtypes = [vp, dp, C.c_int, C.POINTER(PassResult)]
         L.flb_pass_rows.argtypes = [vp, dp, C.c_int, dp, C.c_int, ip]
         L.flb_esikf_update.argtypes = [vp, dp, dp, C.POINTER(UpdateStats)]
@@ -121,6 +122,8 @@ def lib():
         L.flb_neighbors_download.argtypes = [vp, fp, fp, vp, vp, fp, fp]
         L.flb_fov_segment.argtypes = [vp, C.POINTER(FovState), dp, fp, ip, ip]
         L.flb_scan_step.argtypes = [vp, C.POINTER(FovState), fp, C.c_int, C.c_int, dp, dp, C.c_int, C.POINTER(ScanResult)]
+        L.flb_scan_step_begin.argtypes = [vp, C.POINTER(FovState), fp, C.c_int, C.c_int, dp, dp, C.c_int]
+        L.flb_scan_step_finish.argtypes = [vp, C.POINTER(FovState), dp, dp, C.POINTER(ScanResult)]
         L.flb_session_stream.argtypes = [vp]
         L.flb_session_stream.restype = vp
         L.flb_session_sync.argtypes = [vp]
@@ -304,6 +307,11 @@ class Session:
         _chk(lib().flb_scan_upload(self.h, _p(body), len(body), body.strides[0]))
         self.n = len(body)
 
+    def scan_prefetch_ptr(self, ptr, n, stride):
+        """Start the async upload of the NEXT scan (raw host pointer, pinned recommended)."""
+        _chk(lib().flb_scan_prefetch(self.h, C.c_void_p(ptr), int(n), int(stride)))
+        self._pending_n = int(n)
+
     def scan_set_device(self, dev_ptr, n):
         _chk(lib().flb_scan_set_device(self.h, C.c_void_p(dev_ptr), int(n)))
         self.n = int(n)
@@ -364,13 +372,28 @@ class Session:
     def scan_step_ptr(self, fov, ptr, n, stride, state26, P, flg_EKF_inited=True):
         """flb_scan_step on a raw host pointer (e.g. pinned memory owned by the caller); state26/P updated in place."""
         r = ScanResult()
-        self.n = int(n) if ptr else self.n
+        if ptr:
+            self.n = int(n)
+        elif getattr(self, "_pending_n", None) is not None:
+            self.n, self._pending_n = self._pending_n, None
         _chk(lib().flb_scan_step(self.h, C.byref(fov) if fov is not None else None, C.c_void_p(ptr) if ptr else None,
                                  int(n), int(stride), _p(state26), _p(P), 1 if flg_EKF_inited else 0, C.byref(r)))
         return r
 
     def set_update_engine(self, device_driven=True):
         _chk(lib().flb_session_set_update_engine(self.h, 1 if device_driven else 0))
+
+    def scan_step_begin(self, fov, state26, P, flg_EKF_inited=True):
+        """Enqueue the step for the scan made current by scan_upload / scan_set_device / scan_prefetch_ptr."""
+        if getattr(self, "_pending_n", None) is not None:
+            self.n, self._pending_n = self._pending_n, None
+        _chk(lib().flb_scan_step_begin(self.h, C.byref(fov) if fov is not None else None, None, 0, 0, _p(state26), _p(P),
+                                       1 if flg_EKF_inited else 0))
+
+    def scan_step_finish(self, fov, state26, P):
+        r = ScanResult()
+        _chk(lib().flb_scan_step_finish(self.h, C.byref(fov) if fov is not None else None, _p(state26), _p(P), C.byref(r)))
+        return r
 
     def stream_ptr(self):
         return lib().flb_session_stream(self.h)

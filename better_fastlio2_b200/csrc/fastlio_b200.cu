@@ -33,6 +33,15 @@ static int set_err(const char* fmt, ...) {
     if (e__ != cudaSuccess) return set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// destroy paths: never leave a stale error behind for the next call's cudaGetLastError(), but say what happened
+static void quiet(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[fastlio_b200] warning: %s: %s\n", what, cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+}
+#define Q(call) quiet((call), #call)
+
 extern "C" const char* flb_last_error(void) { return g_err; }
 extern "C" const char* flb_version(void) { return "fastlio_b200 0.1 (sm_100a)"; }
 extern "C" int flb_device_count(void) {
@@ -144,6 +153,7 @@ static int fetch_counters(flb_map* m) {
 
 extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   if (!cfg || !out) return set_err("flb_map_create: null argument");
+  cudaGetLastError();  // start from a clean error state
   if (!(cfg->voxel_size > 0.f)) return set_err("flb_map_create: voxel_size must be > 0");
   int ndev = flb_device_count();
   if (ndev <= 0) return set_err("flb_map_create: no CUDA device available (this library has no CPU fallback)");
@@ -195,15 +205,15 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
 
 extern "C" void flb_map_destroy(flb_map* m) {
   if (!m) return;
-  cudaSetDevice(m->cfg.device);
-  if (m->stream) cudaStreamSynchronize(m->stream);
+  Q(cudaSetDevice(m->cfg.device));
+  if (m->stream) Q(cudaStreamSynchronize(m->stream));
   MapDev& d = m->d;
   void* ptrs[] = {d.clist, d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
                   m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
-  for (void* p : ptrs) if (p) cudaFree(p);
-  if (m->h_counters) cudaFreeHost(m->h_counters);
-  for (auto& r : m->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  if (m->stream) cudaStreamDestroy(m->stream);
+  for (void* p : ptrs) if (p) Q(cudaFree(p));
+  if (m->h_counters) Q(cudaFreeHost(m->h_counters));
+  for (auto& r : m->prof_pool) { Q(cudaEventDestroy(r.a)); Q(cudaEventDestroy(r.b)); }
+  if (m->stream) Q(cudaStreamDestroy(m->stream));
   delete m;
 }
 
@@ -629,8 +639,20 @@ struct flb_session {
   cudaStream_t side = nullptr;   // second stream: k_esikf_pre overlaps the measurement kernels of the same pass
   cudaEvent_t ev_fork[8] = {nullptr}, ev_join[8] = {nullptr};
   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [0] update only, [1] update + map_incremental
-  int graph_kernels[2] = {0, 0};
+  cudaGraphExec_t graph_alt[2] = {nullptr, nullptr};  // the same sequences captured for the other body buffer
+  int graph_kernels[2] = {0, 0}, graph_kernels_alt[2] = {0, 0};
   bool use_graph = true;
+  // double-buffered scan upload (flb_scan_prefetch)
+  float4* body_alt = nullptr;
+  unsigned char* raw_alt = nullptr;
+  size_t raw_alt_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  int pending_n = -1;            // >= 0: a prefetched scan waits in body_alt
+  // flb_scan_step_begin / _finish
+  bool step_pending = false, step_device = false;
+  int step_l0 = 0, step_deleted = 0, step_flg = 1;
+  double step_x[26], step_P[NDOF * NDOF];
 };
 
 extern "C" void flb_session_default_config(flb_session_config* c) {
@@ -657,6 +679,7 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); };
   A((void**)&s->body, sizeof(float4) * N);
+  A((void**)&s->body_alt, sizeof(float4) * N);
   A((void**)&s->world, sizeof(float4) * N);
   A((void**)&s->nbr, sizeof(float4) * N * 5);
   A((void**)&s->normvec, sizeof(float4) * N);
@@ -674,6 +697,8 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ctl, sizeof(EsikfCtl));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
   for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&s->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming);
@@ -706,22 +731,26 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
 
 extern "C" void flb_session_destroy(flb_session* s) {
   if (!s) return;
-  cudaSetDevice(s->map->cfg.device);
-  cudaStreamSynchronize(s->map->stream);
-  void* ptrs[] = {s->body, s->world, s->nbr, s->normvec, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
-                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->ctl, s->d_x0P0, s->d_scr};
-  for (void* p : ptrs) if (p) cudaFree(p);
-  if (s->h_out) cudaFreeHost(s->h_out);
-  if (s->h_cnt2) cudaFreeHost(s->h_cnt2);
-  if (s->h_ctl) cudaFreeHost(s->h_ctl);
-  if (s->h_x0P0) cudaFreeHost(s->h_x0P0);
-  for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
-  for (int i = 0; i < 8; ++i) { if (s->ev_fork[i]) cudaEventDestroy(s->ev_fork[i]); if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]); }
-  if (s->side) cudaStreamDestroy(s->side);
-  if (s->ev0) cudaEventDestroy(s->ev0);
-  if (s->ev1) cudaEventDestroy(s->ev1);
-  if (s->ev2) cudaEventDestroy(s->ev2);
-  if (s->ev3) cudaEventDestroy(s->ev3);
+  Q(cudaSetDevice(s->map->cfg.device));
+  Q(cudaStreamSynchronize(s->map->stream));
+  if (s->side) Q(cudaStreamSynchronize(s->side));
+  if (s->copy_stream) Q(cudaStreamSynchronize(s->copy_stream));
+  for (int i = 0; i < 2; ++i) {
+    if (s->graph[i]) Q(cudaGraphExecDestroy(s->graph[i]));
+    if (s->graph_alt[i]) Q(cudaGraphExecDestroy(s->graph_alt[i]));
+  }
+  void* ptrs[] = {s->body, s->body_alt, s->world, s->nbr, s->normvec, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
+                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->raw_alt, s->ctl, s->d_x0P0, s->d_scr};
+  for (void* p : ptrs) if (p) Q(cudaFree(p));
+  if (s->h_out) Q(cudaFreeHost(s->h_out));
+  if (s->h_cnt2) Q(cudaFreeHost(s->h_cnt2));
+  if (s->h_ctl) Q(cudaFreeHost(s->h_ctl));
+  if (s->h_x0P0) Q(cudaFreeHost(s->h_x0P0));
+  cudaEvent_t evs[] = {s->ev0, s->ev1, s->ev2, s->ev3, s->ev_copy};
+  for (cudaEvent_t e : evs) if (e) Q(cudaEventDestroy(e));
+  for (int i = 0; i < 8; ++i) { if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i])); if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i])); }
+  if (s->side) Q(cudaStreamDestroy(s->side));
+  if (s->copy_stream) Q(cudaStreamDestroy(s->copy_stream));
   delete s;
 }
 
@@ -769,6 +798,48 @@ extern "C" int flb_scan_upload(flb_session* s, const float* xyz, int n, int stri
       CU(cudaGetLastError());
     }
   }
+  return scan_reset(s, n);
+}
+
+extern "C" int flb_scan_prefetch(flb_session* s, const float* xyz, int n, int stride) {
+  if (!s) return set_err("null session");
+  if (n < 0 || n > s->cap) return set_err("scan of %d points exceeds max_scan_points=%d", n, s->cap);
+  if (n > 0 && (!xyz || (stride != 12 && stride != 16))) return set_err("flb_scan_prefetch: stride must be 12 or 16");
+  CU(cudaSetDevice(s->map->cfg.device));
+  flb_map* m = s->map;
+  if (n > 0) {
+    if (stride == 16) {
+      CU(cudaMemcpyAsync(s->body_alt, xyz, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->copy_stream));
+    } else {
+      const size_t bytes = (size_t)n * 12;
+      if (bytes > s->raw_alt_cap) {
+        CU(cudaStreamSynchronize(s->copy_stream));
+        if (s->raw_alt) cudaFree(s->raw_alt);
+        s->raw_alt = nullptr; s->raw_alt_cap = 0;
+        CU(cudaMalloc((void**)&s->raw_alt, std::max(bytes, (size_t)1 << 20)));
+        s->raw_alt_cap = std::max(bytes, (size_t)1 << 20);
+      }
+      CU(cudaMemcpyAsync(s->raw_alt, xyz, bytes, cudaMemcpyHostToDevice, s->copy_stream));
+      k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, s->copy_stream>>>(s->raw_alt, 12, s->body_alt, n);
+      m->launches++;
+      CU(cudaGetLastError());
+    }
+  }
+  CU(cudaEventRecord(s->ev_copy, s->copy_stream));
+  s->pending_n = n;
+  return 0;
+}
+// make a prefetched scan current: the processing stream waits for the copy, then the two body buffers swap roles
+static int adopt_prefetched(flb_session* s) {
+  if (s->pending_n < 0) return 0;
+  CU(cudaStreamWaitEvent(s->map->stream, s->ev_copy, 0));
+  std::swap(s->body, s->body_alt);
+  const int n = s->pending_n;
+  s->pending_n = -1;
+  // the captured graphs hold the old body pointer: they are keyed on it
+  for (int i = 0; i < 2; ++i) std::swap(s->graph[i], s->graph_alt[i]);
+  std::swap(s->graph_kernels[0], s->graph_kernels_alt[0]);
+  std::swap(s->graph_kernels[1], s->graph_kernels_alt[1]);
   return scan_reset(s, n);
 }
 
@@ -1063,6 +1134,7 @@ static void stats_from_ctl(const EsikfCtl* c, flb_update_stats* stats) {
 extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_update_stats* stats) {
   if (!s || !state26 || !P) return set_err("flb_esikf_update: null argument");
   CU(cudaSetDevice(s->map->cfg.device));
+  if (adopt_prefetched(s)) return 1;
   if (!s->device_update) return run_update(s, state26, P, stats);
   flb_map* m = s->map;
   CU(cudaEventRecord(s->ev0, m->stream));
@@ -1207,36 +1279,52 @@ extern "C" int flb_fov_segment(flb_map* m, flb_fov_state* fov, const double* pos
 }
 
 // ------------------------------------------------------------------------------------------------ whole scan step
-extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body, int n, int stride, double* state26, double* P,
-                             int flg_EKF_inited, flb_scan_result* out) {
+// begin: everything up to (not including) the synchronisation; finish: synchronise and collect.  A streaming caller puts
+// flb_scan_prefetch(next scan) between the two so the next upload overlaps this scan's kernels.
+extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const float* body, int n, int stride, const double* state26,
+                                   const double* P, int flg_EKF_inited) {
   if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
   flb_map* m = s->map;
   CU(cudaSetDevice(m->cfg.device));
-  const int l0 = m->launches;
-  flb_scan_result r;
-  memset(&r, 0, sizeof(r));
+  s->step_l0 = m->launches;
+  s->step_deleted = 0;
+  s->step_flg = flg_EKF_inited;
+  memcpy(s->step_x, state26, sizeof(s->step_x));
+  memcpy(s->step_P, P, sizeof(s->step_P));
   CU(cudaEventRecord(s->ev2, m->stream));
   if (body) { if (flb_scan_upload(s, body, n, stride)) return 1; }
+  else if (adopt_prefetched(s)) return 1;
   if (fov) {  // laserMapping.cpp:2320 (uses pos_lid of the previous posterior)
     int nb = 0;
-    if (flb_fov_segment(m, fov, fov->pos_lid, nullptr, &nb, &r.n_deleted)) return 1;
+    if (flb_fov_segment(m, fov, fov->pos_lid, nullptr, &nb, &s->step_deleted)) return 1;
   }
-  bool host_path = !s->device_update;
-  double prior_x[26], prior_P[NDOF * NDOF];
-  if (!host_path) {
-    memcpy(prior_x, state26, sizeof(prior_x));
-    memcpy(prior_P, P, sizeof(prior_P));
+  s->step_device = s->device_update;
+  if (s->step_device) {
     CU(cudaEventRecord(s->ev0, m->stream));
     if (launch_scan_device(s, state26, P, flg_EKF_inited, true)) return 1;  // :2380 + :2401, no host round trips inside
     CU(cudaEventRecord(s->ev1, m->stream));
     CU(cudaEventRecord(s->ev3, m->stream));
+  }
+  s->step_pending = true;
+  return 0;
+}
+
+extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* state26, double* P, flb_scan_result* out) {
+  if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
+  if (!s->step_pending) return set_err("flb_scan_step_finish without flb_scan_step_begin");
+  s->step_pending = false;
+  flb_map* m = s->map;
+  CU(cudaSetDevice(m->cfg.device));
+  flb_scan_result r;
+  memset(&r, 0, sizeof(r));
+  r.n_deleted = s->step_deleted;
+  bool host_path = !s->step_device;
+  if (!host_path) {
     CU(cudaStreamSynchronize(m->stream));                  // the single synchronisation of the step
     if (finish_counters(m)) return 1;
     m->has_root = m->has_root || m->h_counters[CNT_VALID] > 0;
     if (s->h_ctl->need_host) {
       host_path = true;                                    // M < 23 branch: redo this scan on the host-driven path
-      memcpy(state26, prior_x, sizeof(prior_x));
-      memcpy(P, prior_P, sizeof(prior_P));
     } else {
       memcpy(state26, s->h_ctl->x, sizeof(double) * 26);
       memcpy(P, s->h_ctl->P, sizeof(double) * NDOF * NDOF);
@@ -1245,8 +1333,10 @@ extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* bo
     }
   }
   if (host_path) {
+    memcpy(state26, s->step_x, sizeof(s->step_x));
+    memcpy(P, s->step_P, sizeof(s->step_P));
     if (run_update(s, state26, P, &r.update)) return 1;  // :2380
-    if (s->n > 0 && enqueue_map_incremental(s, state26, flg_EKF_inited, false)) return 1;  // :2401
+    if (s->n > 0 && enqueue_map_incremental(s, state26, s->step_flg, false)) return 1;  // :2401
     CU(cudaEventRecord(s->ev3, m->stream));
     if (fetch_counters(m)) return 1;
   }
@@ -1259,7 +1349,13 @@ extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* bo
   r.n_no_downsample = s->n > 0 ? s->h_cnt2[1] : 0;
   r.map_valid = m->h_counters[CNT_VALID];
   CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
-  r.kernel_launches = m->launches - l0;
+  r.kernel_launches = m->launches - s->step_l0;
   if (out) *out = r;
   return maybe_rehash(m);
+}
+
+extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body, int n, int stride, double* state26, double* P,
+                             int flg_EKF_inited, flb_scan_result* out) {
+  if (flb_scan_step_begin(s, fov, body, n, stride, state26, P, flg_EKF_inited)) return 1;
+  return flb_scan_step_finish(s, fov, state26, P, out);
 }

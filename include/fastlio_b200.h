@@ -132,6 +132,11 @@ void flb_session_destroy(flb_session* s);
 /* feats_down_body (laserMapping.cpp:2322-2325): upload the voxel-downsampled, undistorted scan (LiDAR frame).
  * Resets the per-scan caches (Nearest_Points, point_selected_surf := true, laserMapping.cpp:2131). */
 int flb_scan_upload(flb_session* s, const float* body_xyz, int n, int stride_bytes);
+/* Asynchronous variant for streaming callers: starts the host->device copy of the NEXT scan on a copy stream into a
+ * second buffer and returns immediately, so the transfer overlaps the processing of the current scan.  The scan
+ * becomes current at the next flb_scan_step / flb_esikf_update called with body == NULL (which waits for the copy).
+ * body_xyz must stay valid (pinned memory recommended) until then; stride 12 or 16 only. */
+int flb_scan_prefetch(flb_session* s, const float* body_xyz, int n, int stride_bytes);
 /* Same, when the scan already lives in device memory as n float4 (x,y,z,*) on the session's device. */
 int flb_scan_set_device(flb_session* s, const void* body_xyz4_dev, int n);
 
@@ -203,6 +208,13 @@ typedef struct flb_scan_result {
  * flb_scan_upload / flb_scan_set_device.  fov may be NULL to skip the fov segment. */
 int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body_xyz, int n, int stride_bytes, double* state26,
                   double* P, int flg_EKF_inited, flb_scan_result* out);
+
+/* The same step split at its single synchronisation point, for streaming callers:
+ *   flb_scan_step_begin(...);  flb_scan_prefetch(next scan);  flb_scan_step_finish(...);
+ * overlaps the upload of the next scan with the kernels of this one. */
+int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const float* body_xyz, int n, int stride_bytes,
+                        const double* state26, const double* P, int flg_EKF_inited);
+int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* state26, double* P, flb_scan_result* out);
 
 /* Stream access for callers that overlap work (returns a cudaStream_t as void*). */
 void* flb_session_stream(flb_session* s);

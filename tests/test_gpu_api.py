@@ -173,3 +173,41 @@ def test_other_sensor_configs_match_oracle(oracle, model, ds, ext, stride):
         assert ok, why
     ses.close()
     t.close()
+
+
+def test_prefetch_and_split_step_equal_plain_step(oracle):
+    """flb_scan_prefetch + flb_scan_step_begin/_finish (double-buffered upload) == flb_scan_step with a host buffer."""
+    import torch
+    scs = [small_scene(seed=s, map_half=25.0, half_extent=80.0) for s in (7, 8, 9)]
+    mp = scs[0]["map"]
+    outs = []
+    for mode in ("plain", "prefetch"):
+        t = capi.KDTree(voxel_size=0.2, max_points=1 << 19, max_blocks=1 << 16)
+        t.Build(mp)
+        ses = capi.Session(t, max_scan_points=40000, max_iterations=3)
+        res = []
+        if mode == "plain":
+            for sc in scs:
+                s, P, r = ses.scan_step(None, sc["body"], sc["prior"], sc["P"], True)
+                res.append((s, P, r.map_valid))
+        else:
+            pins = []
+            for sc in scs:
+                b4 = np.zeros((len(sc["body"]), 4), np.float32)
+                b4[:, :3] = sc["body"]
+                pins.append(torch.from_numpy(b4).pin_memory())
+            ses.scan_prefetch_ptr(pins[0].data_ptr(), len(scs[0]["body"]), 16)
+            for i, sc in enumerate(scs):
+                st = sc["prior"].copy()
+                P = sc["P"].copy()
+                ses.scan_step_begin(None, st, P, True)
+                if i + 1 < len(scs):
+                    ses.scan_prefetch_ptr(pins[i + 1].data_ptr(), len(scs[i + 1]["body"]), 16)
+                r = ses.scan_step_finish(None, st, P)
+                res.append((st, P, r.map_valid))
+        outs.append((res, sort_rows(t.flatten())))
+        ses.close()
+        t.close()
+    for (s0, P0, v0), (s1, P1, v1) in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(s0, s1) and np.array_equal(P0, P1) and v0 == v1
+    assert np.array_equal(outs[0][1], outs[1][1])
