@@ -437,10 +437,132 @@ struct TopKId {
 
 constexpr int STENCIL_THREADS = 128;
 
+// One pass over the candidate voxels recorded in s_cand (per-thread smem column).  PRUNE: skip a voxel (head load and
+// overflow chain) when the squared distance from the query to the voxel's box — a lower bound for every point keyed
+// to that voxel, looked up from per-axis gap tables — already exceeds the current k-th distance.
+template <int K, bool PRUNE>
+__device__ __forceinline__ void stencil_pass(const MapDev& m, const int (*s_blk)[STENCIL_THREADS],
+                                             const unsigned long long (*s_cand)[STENCIL_THREADS],
+                                             const float (*s_gap)[STENCIL_THREADS], int tid, int ox, int oy, int oz, float qx, float qy,
+                                             float qz, float lim, TopKId<K>& t, int& n_head, int& n_chain) {
+  int b = -1, blk = 0;
+  unsigned long long cand = 0ull;
+  for (;;) {
+    unsigned pid[4];
+    int nc = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pid[u] = 0u;
+      for (;;) {
+        while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; blk = s_blk[b][tid]; }
+        if (cand == 0ull) break;
+        const int sl = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        if (PRUNE) {
+          // stencil-relative voxel index per axis (0..4): block half (bit of b) * 4 + local coordinate - stencil origin
+          const int jx = ((b & 1) << 2) + (sl & 3) - ox, jy = (((b >> 1) & 1) << 2) + ((sl >> 2) & 3) - oy, jz = ((b >> 2) << 2) + (sl >> 4) - oz;
+          const float md = s_gap[jx][tid] + s_gap[5 + jy][tid] + s_gap[10 + jz][tid];
+          if (md > t.d[K - 1]) continue;  // no point of this voxel can enter the top-K
+        }
+        pid[u] = (unsigned)blk * 64u + (unsigned)sl;
+        nc = u + 1;
+        break;
+      }
+    }
+    if (nc == 0) break;
+    float4 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nc) e[u] = __ldg(&m.slots[pid[u]]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u < nc) {
+        float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
+        if (dd <= lim) t.insert(dd, pid[u]);
+        ++n_head;
+        int c = __float_as_int(e[u].w);
+        while (c >= 0) {  // overflow chain of this voxel
+          ++n_chain;
+          const float4 o = __ldg(&m.ovf[c]);
+          dd = sqdist(qx, qy, qz, o.x, o.y, o.z);
+          if (dd <= lim) t.insert(dd, 0x80000000u | (unsigned)c);
+          c = __float_as_int(o.w);
+        }
+      }
+    }
+    if (nc < 4) break;
+  }
+}
+
+// Outer-shell pass: (1) a flat, load-free loop tests every occupied shell voxel against the k-th distance known after
+// the inner pass (box lower bound from the per-axis gap tables) and compacts the survivors into a small per-thread list
+// — lanes only diverge on cheap code; (2) the survivors are loaded four at a time.  Returns false if the list overflowed
+// (the query then goes to the exact kernel).
+constexpr int SHELL_LIST = 32;
 template <int K>
-__global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
+__device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, const int (*s_blk)[STENCIL_THREADS],
+                                                   const unsigned long long (*s_cand)[STENCIL_THREADS],
+                                                   const float (*s_gap)[STENCIL_THREADS], unsigned short (*s_list)[STENCIL_THREADS],
+                                                   int tid, int ox, int oy, int oz, float qx, float qy, float qz, float lim,
+                                                   TopKId<K>& t, int& n_head, int& n_chain) {
+  const float bound = t.d[K - 1];
+  int ns = 0;
+  {
+    int b = -1;
+    unsigned long long cand = 0ull;
+    for (;;) {
+      while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; }
+      if (cand == 0ull) break;
+      const int sl = __ffsll((long long)cand) - 1;
+      cand &= cand - 1;
+      const int jx = ((b & 1) << 2) + (sl & 3) - ox, jy = (((b >> 1) & 1) << 2) + ((sl >> 2) & 3) - oy, jz = ((b >> 2) << 2) + (sl >> 4) - oz;
+      const float md = s_gap[jx][tid] + s_gap[5 + jy][tid] + s_gap[10 + jz][tid];
+      if (!(md > bound)) {  // a point of this voxel could still enter the top-K
+        if (ns < SHELL_LIST) s_list[ns][tid] = (unsigned short)((b << 6) | sl);
+        ++ns;
+      }
+    }
+  }
+  if (ns > SHELL_LIST) return false;  // (sparse inner region: hardly anything could be pruned)
+  for (int base = 0; base < ns; base += 4) {
+    unsigned pid[4];
+    float4 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pid[u] = 0u;
+      if (base + u < ns) {
+        const unsigned v = s_list[base + u][tid];
+        pid[u] = (unsigned)s_blk[v >> 6][tid] * 64u + (v & 63u);
+        e[u] = __ldg(&m.slots[pid[u]]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (base + u < ns) {
+        float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
+        if (dd <= lim) t.insert(dd, pid[u]);
+        ++n_head;
+        int c = __float_as_int(e[u].w);
+        while (c >= 0) {  // overflow chain of this voxel
+          ++n_chain;
+          const float4 o = __ldg(&m.ovf[c]);
+          dd = sqdist(qx, qy, qz, o.x, o.y, o.z);
+          if (dd <= lim) t.insert(dd, 0x80000000u | (unsigned)c);
+          c = __float_as_int(o.w);
+        }
+      }
+    }
+  }
+  return true;
+}
+
+template <int K>
+__global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
   __shared__ int s_blk[8][STENCIL_THREADS];
-  __shared__ unsigned long long s_cand[8][STENCIL_THREADS];
+  __shared__ unsigned long long s_cand1[8][STENCIL_THREADS];   // occupied voxels of the inner 3x3x3
+  __shared__ unsigned long long s_cand2[8][STENCIL_THREADS];   // occupied voxels of the outer shell of the 5x5x5
+  __shared__ float s_gap[15][STENCIL_THREADS];                 // squared query-to-slab gaps: x[5], y[5], z[5]
+  __shared__ unsigned short s_list[SHELL_LIST][STENCIL_THREADS];  // surviving shell voxels (block half << 6 | slot)
   const MapDev& m = a.m;
   const int tid = threadIdx.x;
   const int i = blockIdx.x * blockDim.x + tid;
@@ -457,19 +579,31 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
   if (fabsf(qx) < qlim && fabsf(qy) < qlim && fabsf(qz) < qlim) {
     const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
     const int bbx = (cvx - 2) >> 2, bby = (cvy - 2) >> 2, bbz = (cvz - 2) >> 2;
-    // per axis the 5-wide stencil covers local range [o,3] of the low block and [0,(o+4)&3] of the high block
+    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+    // per axis the 5-wide stencil covers local range [o,3] of the low block and [0,o] of the high block; the inner
+    // 3-wide one is the same shifted by one voxel
     const int ox = (cvx - 2) & 3, oy = (cvy - 2) & 3, oz = (cvz - 2) & 3;
-    const unsigned xm2[2] = {(0xFu << ox) & 0xFu, 0xFu >> (3 - ((ox + 4) & 3))};
-    const unsigned ym2[2] = {(0xFu << oy) & 0xFu, 0xFu >> (3 - ((oy + 4) & 3))};
-    const unsigned zm2[2] = {(0xFu << oz) & 0xFu, 0xFu >> (3 - ((oz + 4) & 3))};
-    unsigned ysp2[2];
-    unsigned long long zsp2[2];
+    unsigned x5[2], y5[2], z5[2], x3[2], y3[2], z3[2];
+    {
+      const unsigned mx5 = 31u << ox, my5 = 31u << oy, mz5 = 31u << oz, mx3 = 14u << ox, my3 = 14u << oy, mz3 = 14u << oz;
+      x5[0] = mx5 & 15u; x5[1] = (mx5 >> 4) & 15u; y5[0] = my5 & 15u; y5[1] = (my5 >> 4) & 15u; z5[0] = mz5 & 15u; z5[1] = (mz5 >> 4) & 15u;
+      x3[0] = mx3 & 15u; x3[1] = (mx3 >> 4) & 15u; y3[0] = my3 & 15u; y3[1] = (my3 >> 4) & 15u; z3[0] = mz3 & 15u; z3[1] = (mz3 >> 4) & 15u;
+    }
+    auto spread_y = [](unsigned ym) { return (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9); };  // bits 0,4,8,12
+    auto spread_z = [](unsigned zm) {
+      return (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) | ((unsigned long long)(zm & 4u) << 30) |
+             ((unsigned long long)(zm & 8u) << 45);                                                                      // bits 0,16,32,48
+    };
+    // squared gaps from the query to the 5 voxel slabs per axis (conservative: shrunk by the rounding margin)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const unsigned ym = ym2[h], zm = zm2[h];
-      ysp2[h] = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);  // bits 0,4,8,12
-      zsp2[h] = (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) | ((unsigned long long)(zm & 4u) << 30) |
-                ((unsigned long long)(zm & 8u) << 45);                               // bits 0,16,32,48
+    for (int j = 0; j < 5; ++j) {
+      const float lx = (float)(cvx - 2 + j) * ds, ly = (float)(cvy - 2 + j) * ds, lz = (float)(cvz - 2 + j) * ds;
+      const float gx = fmaxf(fmaxf(lx - qx, qx - (lx + ds)) - mg, 0.f);
+      const float gy = fmaxf(fmaxf(ly - qy, qy - (ly + ds)) - mg, 0.f);
+      const float gz = fmaxf(fmaxf(lz - qz, qz - (lz + ds)) - mg, 0.f);
+      s_gap[j][tid] = gx * gx;
+      s_gap[5 + j][tid] = gy * gy;
+      s_gap[10 + j][tid] = gz * gz;
     }
     // ---- the 8 hash probes are INDEPENDENT loads: issue them back to back (memory-level parallelism), then resolve;
     // only a collision (first slot holds another key) falls back to the sequential probe loop
@@ -492,57 +626,22 @@ __global__ void __launch_bounds__(STENCIL_THREADS) k_knn_stencil(KnnArgs a) {
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       const int hx = b & 1, hy = (b >> 1) & 1, hz = b >> 2;
+      const unsigned long long sten5 = (unsigned long long)(x5[hx] * spread_y(y5[hy])) * spread_z(z5[hz]);
+      const unsigned long long sten3 = (unsigned long long)(x3[hx] * spread_y(y3[hy])) * spread_z(z3[hz]);
       s_blk[b][tid] = blk8[b];
-      s_cand[b][tid] = occ[b] & ((unsigned long long)(xm2[hx] * ysp2[hy]) * zsp2[hz]);
+      s_cand1[b][tid] = occ[b] & sten3;
+      s_cand2[b][tid] = occ[b] & sten5 & ~sten3;
     }
-    // ---- one loop over all candidates of this thread (own smem column: no synchronisation needed), four point
-    // loads in flight per round
-    int b = -1, blk = 0;
+    // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
-    unsigned long long cand = 0ull;
-    for (;;) {
-      unsigned pid[4];
-      int nc = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; blk = s_blk[b][tid]; }
-        pid[u] = 0u;
-        if (cand != 0ull) {
-          const int sl = __ffsll((long long)cand) - 1;
-          cand &= cand - 1;
-          pid[u] = (unsigned)blk * 64u + (unsigned)sl;
-          nc = u + 1;
-        }
-      }
-      if (nc == 0) break;
-      float4 e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (u < nc) e[u] = __ldg(&m.slots[pid[u]]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (u < nc) {
-          float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
-          if (dd <= lim) t.insert(dd, pid[u]);
-          ++n_head;
-          int c = __float_as_int(e[u].w);
-          while (c >= 0) {  // overflow chain of this voxel
-            ++n_chain;
-            const float4 o = __ldg(&m.ovf[c]);
-            dd = sqdist(qx, qy, qz, o.x, o.y, o.z);
-            if (dd <= lim) t.insert(dd, 0x80000000u | (unsigned)c);
-            c = __float_as_int(o.w);
-          }
-        }
-      }
-      if (nc < 4) break;
-    }
+    stencil_pass<K, false>(m, s_blk, s_cand1, s_gap, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain);
+    if (!stencil_shell_pass<K>(m, s_blk, s_cand2, s_gap, s_list, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain))
+      stencil_pass<K, false>(m, s_blk, s_cand2, s_gap, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain);  // list overflow: visit all
     if (a.phase_stats) {  // profiling only: candidate statistics
       atomicAdd(&a.phase_stats[4], n_chain);
       atomicMax(&a.phase_stats[5], n_chain);
       atomicAdd(&a.phase_stats[6], n_head);
     }
-    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
     const float cov = cover2(qx, qy, qz, (float)(cvx - 2) * ds, (float)(cvy - 2) * ds, (float)(cvz - 2) * ds,
                              (float)(cvx + 3) * ds, (float)(cvy + 3) * ds, (float)(cvz + 3) * ds, mg);
     done = (t.d[K - 1] < CUDART_INF_F && t.d[K - 1] < cov) || cov > lim;
