@@ -18,6 +18,7 @@
 namespace flb {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int BLOCK_RINGS = 3;  // block shells searched by the exact kernel before it falls back to the coarse levels
 
 template <int K>
 struct TopK {
@@ -254,7 +255,7 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
       const int bit = k * 64 + h * 32 + lane;
       const int bx = ccx * 8 + (bit & 7), by = ccy * 8 + ((bit >> 3) & 7), bz = ccz * 8 + (bit >> 6);
       bool go = (word >> (h * 32 + lane)) & 1ull;
-      if (go && abs(bx - qbx_) <= 1 && abs(by - qby_) <= 1 && abs(bz - qbz_) <= 1) go = false;  // visited by phase B0
+      if (go && abs(bx - qbx_) <= BLOCK_RINGS && abs(by - qby_) <= BLOCK_RINGS && abs(bz - qbz_) <= BLOCK_RINGS) go = false;  // visited by phase B0
       if (go) {
         const float lx = (float)bx * bs, ly = (float)by * bs, lz = (float)bz * bs;
         const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs, ly + bs, lz + bs, mg);
@@ -321,25 +322,41 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
       bool done = (gcount == K && thr < cov) || cov > lim;
       const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
       if (!done) {
-        // ---------------- phase B0: the 3x3x3 BLOCKS around the query block (one block per lane): covers >= 4 voxels
-        // around the query, enough for almost every query the stencil could not settle, and gives phase B a finite bound
+        // ---------------- phase B0: shells of BLOCKS around the query block, radius 1..BLOCK_RINGS (one shell block per
+        // lane and round, hash probes in parallel, candidates scanned co-operatively).  Ring r covers >= 4r voxels around
+        // the query; ring 3 (2.4 m at 0.2 m voxels) exceeds the 5 m^2 acceptance radius of h_share_model, so only
+        // genuinely far queries (map frontier) go on to the coarse levels.
         phase = 1;
-        {
-          int bx = 0, by = 0, bz = 0, blk = -1;
-          unsigned long long mask = 0ull;
-          if (lane < 27) {
-            bx = qbx + (lane % 3) - 1; by = qby + ((lane / 3) % 3) - 1; bz = qbz + (lane / 9) - 1;
-            blk = find_block(m, pack_key(bx, by, bz));
-            if (blk >= 0) mask = __ldg(&m.bmask[blk]);
-          }
-          const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
-          coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, true, fminf(lim, thr), t);
-        }
-        gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
         const float bs4 = 4.f * ds;
-        cov = cover2(qx, qy, qz, (float)(qbx - 1) * bs4, (float)(qby - 1) * bs4, (float)(qbz - 1) * bs4,
-                     (float)(qbx + 2) * bs4, (float)(qby + 2) * bs4, (float)(qbz + 2) * bs4, mg);
-        done = (gcount == K && thr < cov) || cov > lim;
+#pragma unroll 1
+        for (int r = 1; r <= BLOCK_RINGS && !done; ++r) {
+          const int w = 2 * r + 1, nb = w * w * w;
+          const float bound = gcount == K ? thr : CUDART_INF_F;
+#pragma unroll 1
+          for (int base = 0; base < nb; base += 32) {
+            const int idx = base + lane;
+            int bx = 0, by = 0, bz = 0, blk = -1;
+            unsigned long long mask = 0ull;
+            if (idx < nb) {
+              const int dx = idx % w - r, dy = (idx / w) % w - r, dz = idx / (w * w) - r;
+              if (max(abs(dx), max(abs(dy), abs(dz))) == r) {  // shell only: the interior was visited by smaller rings
+                bx = qbx + dx; by = qby + dy; bz = qbz + dz;
+                const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
+                const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);
+                if (!(md > bound || md > lim)) {
+                  blk = find_block(m, pack_key(bx, by, bz));
+                  if (blk >= 0) mask = __ldg(&m.bmask[blk]);
+                }
+              }
+            }
+            const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
+            if (todo) coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, r == 1, fminf(lim, bound), t);
+          }
+          gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
+          cov = cover2(qx, qy, qz, (float)(qbx - r) * bs4, (float)(qby - r) * bs4, (float)(qbz - r) * bs4,
+                       (float)(qbx + r + 1) * bs4, (float)(qby + r + 1) * bs4, (float)(qbz + r + 1) * bs4, mg);
+          done = (gcount == K && thr < cov) || cov > lim;
+        }
       }
       if (!done) {
         // ---------------- phase B: 3x3x3 coarse cells around the query (blocks of B0 are skipped inside)
