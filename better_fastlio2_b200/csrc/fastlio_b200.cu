@@ -86,6 +86,7 @@ struct flb_map {
   int* h_counters = nullptr;     // pinned mirror of counters
   int* d_misc = nullptr;         // misc device ints (out counts, range)
   int launches = 0;              // kernel launch counter (cumulative)
+  int refs = 1;                  // the map handle + every live session: storage is freed when the last one goes
   // optional per-kernel-class CUDA-event timing (flb_map_profile_*)
   bool prof_on = false;
   bool capturing = false;        // inside cudaStreamBeginCapture: no event timing, no allocations
@@ -203,8 +204,13 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   return 0;
 }
 
+static void map_release(flb_map* m);
 extern "C" void flb_map_destroy(flb_map* m) {
   if (!m) return;
+  map_release(m);  // sessions created on this map keep it alive until they are destroyed too
+}
+static void map_release(flb_map* m) {
+  if (--m->refs > 0) return;
   Q(cudaSetDevice(m->cfg.device));
   if (m->stream) Q(cudaStreamSynchronize(m->stream));
   MapDev& d = m->d;
@@ -672,6 +678,7 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   flb_session* s = new (std::nothrow) flb_session();
   if (!s) return set_err("out of host memory");
   s->map = m;
+  m->refs++;
   s->cfg = *cfg;
   s->cap = cfg->max_scan_points;
   const size_t N = (size_t)s->cap;
@@ -751,7 +758,9 @@ extern "C" void flb_session_destroy(flb_session* s) {
   for (int i = 0; i < 8; ++i) { if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i])); if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i])); }
   if (s->side) Q(cudaStreamDestroy(s->side));
   if (s->copy_stream) Q(cudaStreamDestroy(s->copy_stream));
+  flb_map* m = s->map;
   delete s;
+  map_release(m);
 }
 
 extern "C" int flb_session_set_update_engine(flb_session* s, int device_driven) {

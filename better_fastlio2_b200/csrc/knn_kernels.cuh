@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
             unsigned long long mask = 0ull;
             if (idx < nb) {
               const int dx = idx % w - r, dy = (idx / w) % w - r, dz = idx / (w * w) - r;
-              if (max(abs(dx), max(abs(dy), abs(dz))) == r) {  // shell only: the interior was visited by smaller rings
+              // shell only — the interior was visited by smaller rings; ring 1 also takes the query's own block, whose
+              // voxels outside the 5x5x5 stencil have not been seen yet
+              if (r == 1 || max(abs(dx), max(abs(dy), abs(dz))) == r) {
                 bx = qbx + dx; by = qby + dy; bz = qbz + dz;
                 const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
                 const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);

@@ -211,3 +211,15 @@ def test_prefetch_and_split_step_equal_plain_step(oracle):
     for (s0, P0, v0), (s1, P1, v1) in zip(outs[0][0], outs[1][0]):
         assert np.array_equal(s0, s1) and np.array_equal(P0, P1) and v0 == v1
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_map_destroyed_before_session_is_safe(scene):
+    """The map is reference counted by its sessions: destroying the KD_TREE handle first must not crash."""
+    t = capi.KDTree(voxel_size=0.2, max_points=1 << 19, max_blocks=1 << 16)
+    t.Build(scene["map"][:50000])
+    ses = capi.Session(t, max_scan_points=1000, max_iterations=3)
+    ses.scan_upload(scene["body"][:1000])
+    t.close()                       # handle gone, storage kept alive by the session
+    s, P, st = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
+    assert st["passes"] == 4
+    ses.close()
