@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfastlio_b200.so")
+# FLB_LIB selects another build of the SAME library (debug/trace or A/B kernel variants); there is still no CPU fallback
+LIB_PATH = os.environ.get("FLB_LIB") or os.path.join(_HERE, "libfastlio_b200.so")
 
 NACC_DOF = 23
 

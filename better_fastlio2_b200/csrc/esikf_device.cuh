@@ -38,7 +38,7 @@ __device__ __forceinline__ void mm3(const double* A, const double* B, double* C)
 }
 __device__ __forceinline__ void cos_sinc_sqrt(double x2, double& c, double& s) {  // mtkmath.hpp:142-174
   const double bound = 1.220703125e-4;  // sqrt(sqrt(eps))
-  if (x2 >= bound) { const double x = sqrt(x2); c = cos(x); s = sin(x) / x; return; }
+  if (x2 >= bound) { const double x = sqrt(x2); double sn; sincos(x, &sn, &c); s = sn / x; return; }
   const double inv[7] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
   double cosi = 1., sinc = 1., term = -1 / 2. * x2;
   for (int i = 0; i < 3; ++i) { cosi += term; term *= inv[2 * i]; sinc += term; term *= -inv[2 * i + 1] * x2; }
@@ -65,7 +65,9 @@ __device__ __noinline__ void A_matrix_T(const double* v, double* J) {  // A_matr
     double H[9], HH[9];
     hat(v, H);
     mm3(H, H, HH);
-    const double a = (1 - cos(n)) / sq, b = (1 - sin(n) / n) / sq;
+    double sn, cn;
+    sincos(n, &sn, &cn);
+    const double a = (1 - cn) / sq, b = (1 - sn / n) / sq;
     for (int i = 0; i < 9; ++i) A[i] = A[i] + a * H[i] + b * HH[i];
   }
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J[3 * i + j] = A[3 * j + i];
@@ -112,28 +114,31 @@ __device__ __noinline__ void s2_Mx(const double* xpg, const double* delta, doubl
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += T2[3 * i + k] * Bp[2 * k + j]; Mx[2 * i + j] = s; }
   }
 }
-// Gauss-Jordan inverse of a symmetric positive definite 23x23 matrix in shared memory, block-wide and COMPACT (a
-// rolled 23-sweep loop: this kernel runs once per launch, so straight-line unrolled code would be instruction-fetch
-// bound).  No pivoting is needed for SPD input (both matrices inverted per pass are: P/R and (P/R)^-1 + H^T H).
-// Ping-pong between buf0 and buf1 (one barrier per sweep); the result ends in buf1 (23 is odd).
-__device__ __noinline__ void b_inverse_spd(double* buf0, double* buf1, int tid) {
+// Gauss-Jordan inverse of a symmetric positive definite N x N matrix in shared memory, block-wide and COMPACT (a
+// rolled N-sweep loop: this kernel runs once per launch, so straight-line unrolled code would be instruction-fetch
+// bound).  No pivoting is needed for SPD input.  Ping-pong between buf0 and buf1 (one barrier per sweep); returns the
+// buffer holding the result (buf1 for odd N, buf0 for even N).
+template <int N>
+__device__ __noinline__ double* b_inverse_spd(double* buf0, double* buf1, int tid) {
+  static_assert(N * N <= ESIKF_THREADS, "one element per thread");
   double* cur = buf0;
   double* nxt = buf1;
+  const int i = tid / N, j = tid - i * N;   // this thread's element (fixed over the sweeps)
+  const bool act = tid < N * N;
 #pragma unroll 1
-  for (int k = 0; k < NDOF; ++k) {
-    const double inv = 1.0 / cur[k * NDOF + k];
-#pragma unroll 1
-    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) {
-      const int i = e / NDOF, j = e - i * NDOF;
+  for (int k = 0; k < N; ++k) {
+    const double inv = __drcp_rn(cur[k * N + k]);   // IEEE round-to-nearest reciprocal == 1.0 / x, without the division call
+    if (act) {
       double v;
-      if (i == k) v = (j == k) ? inv : cur[k * NDOF + j] * inv;
-      else if (j == k) v = -(cur[i * NDOF + k] * inv);
-      else v = cur[e] - cur[i * NDOF + k] * (cur[k * NDOF + j] * inv);
-      nxt[e] = v;
+      if (i == k) v = (j == k) ? inv : cur[k * N + j] * inv;
+      else if (j == k) v = -(cur[i * N + k] * inv);
+      else v = cur[tid] - cur[i * N + k] * (cur[k * N + j] * inv);
+      nxt[tid] = v;
     }
     __syncthreads();
     double* t = cur; cur = nxt; nxt = t;
   }
+  return cur;
 }
 
 // J (2x2) = Nx_yy(xg) * Mx(xpg, delta)   (S2.hpp:259-280, esekfom.hpp:1693-1695)
@@ -320,18 +325,21 @@ __device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double*
 
 // Load the propagated state / covariance for a new scan.
 // staging layout: x0[26] | P0[529] | n | flg_EKF_inited   (all doubles, so one H2D copy carries a scan's inputs)
-__global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage) {
+__global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage, int* work_counts) {
+  FLB_TRACE_BEGIN(0);
   const double* x0 = stage;
   const double* P0 = stage + 26;
   const int n = (int)stage[26 + NDOF * NDOF];
   for (int i = threadIdx.x; i < NDOF * NDOF; i += blockDim.x) { c->Pp[i] = P0[i]; c->P[i] = P0[i]; }
   if (threadIdx.x < 26) { c->x[threadIdx.x] = x0[threadIdx.x]; c->xp[threadIdx.x] = x0[threadIdx.x]; }
+  if (threadIdx.x >= 32 && threadIdx.x < 40) work_counts[threadIdx.x - 32] = 0;   // per-pass k-NN work-list counters
   __syncthreads();
   if (threadIdx.x == 0) {
     c->it = -1; c->t = 0; c->converge = 1; c->finished = 0; c->need_host = 0; c->passes = 0; c->searches = 0;
     c->lastM = 0; c->last_res = 0.0; c->n = n; c->flg_inited = (int)stage[26 + NDOF * NDOF + 1];
     dev::pose_from_state(c->x, c->pose);
   }
+  FLB_TRACE_END(0);
 }
 
 // One loop iteration of update_iterated_dyn_share_modified is split in two kernels so that the half that only needs
@@ -342,17 +350,30 @@ __global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage) {
 // Both are latency-oriented: loop flags / state staged in shared memory with parallel loads, transcendental-heavy
 // sub-manifold work spread over warps, compact rolled loops (a kernel that runs once per launch is instruction-fetch
 // bound on straight-line code).
+// The gain is formed in the 12-dimensional subspace the measurement touches instead of through the two 23x23 inverses
+// of esekfom.hpp:1788/1808.  With Pr = P/R (projected), U = [I12; 0], S = H^T H (12x12, zero elsewhere):
+//   P_inv[:, 0:12] = ((Pr)^-1 + U S U^T)^-1 U = Pr[:, 0:12] (I + S Pr11)^-1 = Q (T11 + S)^-1,
+//   T11 = Pr11^-1,  Q = Pr[:, 0:12] T11          (both only depend on the iterate: k_esikf_pre, off the critical path)
+// so K_x[:, 0:12] = P_inv[:, 0:12] S and K_h = P_inv[:, 0:12] H^T h (esekfom.hpp:1810-1815) need ONE 12x12 SPD inverse
+// after the reduction.  Without extrinsic estimation the Jacobian columns 6..11 are identically zero
+// (laserMapping.cpp:1996), so the same identities hold with U = [I6; 0]: MD = 6 and a 6x6 inverse (K_x[:, 6:12] = 0).  Algebraically identical to the reference's information form, better conditioned, and it agrees
+// with the host engine (which keeps the reference's two-inverse form) to ~1e-16 (tests/test_gpu_parity.py).
 struct EsikfScratch {
   double dxn[NDOF];
   double P[NDOF * NDOF];   // projected P_propagated
-  double T[NDOF * NDOF];   // (P/R)^-1
+  double T11[144];         // (P[0:12,0:12] / R)^-1
+  double Q[NDOF * 12];     // (P[:,0:12] / R) T11
 };
 
+template <int MD>
 __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl* c, EsikfScratch* sc) {
   using namespace dev;
-  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[NDOF * NDOF];
+  __shared__ double P[NDOF * NDOF], L[144], T[144];
   __shared__ double dx[NDOF], J3a[9], J3b[9], J2[4], Nx[6], Mx[6], xs[26], xps[26];
   const int tid = threadIdx.x;
+  FLB_TRACE_BEGIN(1 * 8 + c->it + 1);
+  const int trace_slot = 1 * 8 + c->it + 1;
+  (void)trace_slot;
   if (c->finished || c->it >= c->max_iter || c->n <= 0) return;   // uniform
   if (tid >= 32 && tid < 58) { xs[tid - 32] = c->x[tid - 32]; xps[tid - 32] = c->xp[tid - 32]; }
   for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) P[e] = c->Pp[e];
@@ -392,48 +413,70 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
   b_mul_cols_T<3>(P, 6, J3b, tid);
   b_mul_rows<2>(P, P, 21, J2, tid);                     // S2 block :1683-1703
   b_mul_cols_T<2>(P, 21, J2, tid);
-  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) { L[e] = P[e] / R; sc->P[e] = P[e]; }
+  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) sc->P[e] = P[e];
+  if (tid < MD * MD) L[tid] = P[(tid / MD) * NDOF + (tid % MD)] / R;   // Pr11 (MD x MD)
   __syncthreads();
-  b_inverse_spd(L, T, tid);                             // (P/R)^-1 -> T   (:1788)
-  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) sc->T[e] = T[e];
+  const double* T11 = b_inverse_spd<MD>(L, T, tid);                    // Pr11^-1
+  if (tid < MD * MD) sc->T11[tid] = T11[tid];
+  for (int e = tid; e < NDOF * MD; e += ESIKF_THREADS) {               // Q = Pr[:, 0:MD] T11
+    const int i = e / MD, j = e - i * MD;
+    double q = 0;
+    for (int k = 0; k < MD; ++k) q += (P[i * NDOF + k] / R) * T11[k * MD + j];
+    sc->Q[e] = q;
+  }
+  FLB_TRACE_END(trace_slot);
 }
 
+template <int MD>
 __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, const double* __restrict__ partial, int nblocks,
                                                                     const EsikfScratch* __restrict__ sc) {
   using namespace dev;
-  __shared__ double acc[96];
-  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[NDOF * NDOF];
+  __shared__ double acc[96], acc2[96];
+  __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[144], Q[NDOF * 12], Y[156];
   __shared__ double Kx[NDOF * 12], HTH[144], HTh[12], Kh[NDOF], lim[NDOF];
   __shared__ double dxn[NDOF], dx_[NDOF], J3a[9], J3b[9], J2[4], Nx[6], Mx[6], xs[26], xps[26];
   __shared__ int s_i[8];   // finished, it, max_iter, n, t, converge
   __shared__ int s_fin, s_conv, s_tt;
   const int tid = threadIdx.x;
+  const int trace_pass = c->it + 1;
+  (void)trace_pass;
+  FLB_TRACE_BEGIN(5 * 8 + trace_pass);
+  FLB_TRACE_PHASE(trace_pass * 12 + 0);
   if (tid == 0) s_i[0] = c->finished; else if (tid == 1) s_i[1] = c->it; else if (tid == 2) s_i[2] = c->max_iter;
   else if (tid == 3) s_i[3] = c->n; else if (tid == 4) s_i[4] = c->t; else if (tid == 5) s_i[5] = c->converge;
   if (tid >= 32 && tid < 58) { xs[tid - 32] = c->x[tid - 32]; xps[tid - 32] = c->xp[tid - 32]; }
   if (tid >= 64 && tid < 64 + NDOF) { lim[tid - 64] = c->limit[tid - 64]; dxn[tid - 64] = sc->dxn[tid - 64]; }
-  // ---- fixed-order reduction of the per-block partials (role of K2): 2 threads per entry (halves of the block range),
-  // 16 independent loads in flight per thread
+  // ---- the matrices k_esikf_pre left for this pass: their loads are issued first and complete under the reduction
+  double pP[3], pQ[2];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) { const int e = tid + u * ESIKF_THREADS; pP[u] = e < NDOF * NDOF ? sc->P[e] : 0.0; }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int e = tid + u * ESIKF_THREADS; pQ[u] = e < NDOF * MD ? sc->Q[e] : 0.0; }
+  const double pT = tid < MD * MD ? sc->T11[tid] : 0.0;
+  // ---- fixed-order reduction of the per-block partials (role of K2): 2 threads per entry (halves of the block range,
+  // coalesced across the entries), 37 independent loads in flight per thread
   {
-    const int e = tid >> 1, h = tid & 1;
+    const int e = tid & 127, h = tid >> 7;
     double s = 0.0;
     if (e < NACC) {
       const int half = (nblocks + 1) >> 1;
       const int b0 = h ? half : 0, b1 = h ? nblocks : half;
       int b = b0;
-      for (; b + 16 <= b1; b += 16) {
-        double v[16];
+      for (; b + 37 <= b1; b += 37) {
+        double v[37];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = partial[(size_t)(b + u) * NACC + e];
+        for (int u = 0; u < 37; ++u) v[u] = partial[(size_t)(b + u) * NACC + e];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) s += v[u];
+        for (int u = 0; u < 37; ++u) s += v[u];
       }
       for (; b < b1; ++b) s += partial[(size_t)b * NACC + e];
+      if (h) acc2[e] = s;
     }
-    const double o = __shfl_xor_sync(FULL, s, 1);
-    if (e < NACC && h == 0) acc[e] = s + o;
+    __syncthreads();
+    if (e < NACC && h == 0) acc[e] = s + acc2[e];
   }
   __syncthreads();
+  FLB_TRACE_PHASE(trace_pass * 12 + 1);   // partials reduced
   const int it = s_i[1], max_iter = s_i[2];
   if (s_i[0] || it >= max_iter) return;                                          // loop already ended
   if (s_i[3] <= 0) { if (tid == 0) { c->it = it + 1; c->passes++; } return; }    // empty scan: every pass invalid
@@ -442,24 +485,38 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, 
   if (M < 1) { if (tid == 0) c->it = it + 1; return; }                            // valid = false -> continue (:1641-1644)
   if (M < NDOF) { if (tid == 0) { c->need_host = 1; c->finished = 1; } return; }  // under-determined branch: host path
   if (tid == 0) { c->lastM = M; c->last_res = acc[91]; }
-  if (tid < 144) {
-    const int i = tid / 12, j = tid - i * 12;
+  // gain in the measured subspace (see EsikfScratch): V = (T11 + H^T H)^-1, Y = V [H^T H | H^T h], [K_x | K_h] = Q Y
+  if (tid < MD * MD) {
+    const int i = tid / MD, j = tid - i * MD;
     const int a = i < j ? i : j, b = i < j ? j : i;
-    HTH[tid] = acc[a * 13 - a * (a - 1) / 2 + (b - a)];
+    const double hth = acc[a * 13 - a * (a - 1) / 2 + (b - a)];
+    HTH[tid] = hth;                                         // MD x MD
+    T[tid] = pT + hth;
   }
-  if (tid >= 160 && tid < 172) { const int l = tid - 160; HTh[l] = acc[l * 13 - l * (l - 1) / 2 + (12 - l)]; }
-  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) { P[e] = sc->P[e]; T[e] = sc->T[e]; }
+  if (tid >= 160 && tid < 160 + MD) { const int l = tid - 160; HTh[l] = acc[l * 13 - l * (l - 1) / 2 + (12 - l)]; }
+#pragma unroll
+  for (int u = 0; u < 3; ++u) { const int e = tid + u * ESIKF_THREADS; if (e < NDOF * NDOF) P[e] = pP[u]; }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int e = tid + u * ESIKF_THREADS; if (e < NDOF * MD) Q[e] = pQ[u]; }
   __syncthreads();
-  // information form :1790-1815
-  if (tid < 144) T[(tid / 12) * NDOF + (tid % 12)] += HTH[tid];
-  __syncthreads();
-  b_inverse_spd(T, L, tid);                             // P_inv -> L
-  if (tid < NDOF) { double s = 0; for (int k = 0; k < 12; ++k) s += L[tid * NDOF + k] * HTh[k]; Kh[tid] = s; }
-  for (int e = tid; e < NDOF * 12; e += ESIKF_THREADS) {
-    const int i = e / 12, b = e - i * 12;
+  FLB_TRACE_PHASE(trace_pass * 12 + 2);   // matrices staged
+  const double* V = b_inverse_spd<MD>(T, L, tid);
+  FLB_TRACE_PHASE(trace_pass * 12 + 3);   // inverse done
+  if (tid < MD * (MD + 1)) {
+    const int i = tid / (MD + 1), j = tid - i * (MD + 1);
     double q = 0;
-    for (int k = 0; k < 12; ++k) q += L[i * NDOF + k] * HTH[k * 12 + b];
-    Kx[e] = q;
+    for (int k = 0; k < MD; ++k) q += V[i * MD + k] * (j < MD ? HTH[k * MD + j] : HTh[k]);
+    Y[tid] = q;
+  }
+  __syncthreads();
+  for (int e = tid; e < NDOF * 13; e += ESIKF_THREADS) {      // K_x (23 x 12, columns >= MD are zero) and K_h
+    const int i = e / 13, j = e - i * 13;
+    double q = 0;
+    if (j < MD || j == 12) {
+      const int jj = j == 12 ? MD : j;
+      for (int k = 0; k < MD; ++k) q += Q[i * MD + k] * Y[k * (MD + 1) + jj];
+    }
+    if (j < 12) Kx[i * 12 + j] = q; else Kh[i] = q;
   }
   __syncthreads();
   if (tid < NDOF) {                                     // :1821 dx_ = K_h + (K_x - I) dx_new
@@ -468,6 +525,7 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, 
     dx_[tid] = Kh[tid] + s;
   }
   __syncthreads();
+  FLB_TRACE_PHASE(trace_pass * 12 + 4);   // gain and dx_ done
   // convergence test (:1824-1838) first: the Jacobians of the final covariance are only needed on the last pass
   if (tid == 0) {
     int conv = 1, tt = s_i[4];
@@ -497,6 +555,7 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, 
   if (tid < 4 && s_fin) { const int i = tid >> 1, j = tid & 1; double s = 0; for (int k = 0; k < 3; ++k) s += Nx[3 * i + k] * Mx[2 * k + j]; J2[tid] = s; }
   __syncthreads();
   const int fin = s_fin;
+  FLB_TRACE_PHASE(trace_pass * 12 + 5);   // boxplus (+ final Jacobians) done
   if (fin) {                                            // :1841-1931
     for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) L[e] = P[e];
     __syncthreads();
@@ -532,6 +591,8 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, 
   if (tid < 26) c->x[tid] = xs[tid];
   if (tid == 32) { c->converge = s_conv; c->t = s_tt; c->finished = fin; c->it = it + 1; }
   if (tid == 64) pose_from_state(xs, c->pose);
+  FLB_TRACE_PHASE(trace_pass * 12 + 6);   // covariance / state written
+  FLB_TRACE_END(5 * 8 + trace_pass);
 }
 
 }  // namespace flb

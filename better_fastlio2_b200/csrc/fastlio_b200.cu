@@ -127,6 +127,7 @@ static int map_reset_storage(flb_map* m) {
   CU(cudaMemsetAsync(d.bmask, 0, sizeof(uint64_t) * d.block_cap, st));
   CU(cudaMemsetAsync(d.slots, 0xFF, sizeof(float4) * 64 * (size_t)d.block_cap, st));
   CU(cudaMemsetAsync(d.bkey, 0xFF, sizeof(uint64_t) * d.block_cap, st));
+  CU(cudaMemsetAsync(d.brel, 0, sizeof(uint64_t) * d.block_cap, st));
   CU(cudaMemsetAsync(d.ckeys, 0xFF, sizeof(uint64_t) * m->chash_cap, st));
   CU(cudaMemsetAsync(d.cbits, 0, sizeof(uint64_t) * 8 * (size_t)m->chash_cap, st));
   int init[CNT_COUNT];
@@ -183,13 +184,14 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   rc |= dev_alloc(m, (void**)&d.slots, sizeof(float4) * 64 * (size_t)d.block_cap);
   rc |= dev_alloc(m, (void**)&d.ovf, sizeof(float4) * (size_t)d.ovf_cap);
   rc |= dev_alloc(m, (void**)&d.bkey, sizeof(uint64_t) * d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.brel, sizeof(uint64_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.free_blk, sizeof(uint32_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.free_ovf, sizeof(uint32_t) * d.ovf_cap);
   rc |= dev_alloc(m, (void**)&d.ckeys, sizeof(uint64_t) * m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.cbits, sizeof(uint64_t) * 8 * (size_t)m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.clist, sizeof(uint32_t) * (size_t)m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.counters, sizeof(int) * CNT_COUNT);
-  rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 16);
+  rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 32);   // [0..3] counts, [4..9] range, [12] work count, [16..23] per-pass work counts
   rc |= dev_alloc(m, (void**)&m->d_phase, sizeof(int) * 8);
   if (rc) { flb_map_destroy(m); return 1; }
   if (cudaMallocHost((void**)&m->h_counters, sizeof(int) * CNT_COUNT) != cudaSuccess) { flb_map_destroy(m); return set_err("cudaMallocHost failed"); }
@@ -214,7 +216,7 @@ static void map_release(flb_map* m) {
   Q(cudaSetDevice(m->cfg.device));
   if (m->stream) Q(cudaStreamSynchronize(m->stream));
   MapDev& d = m->d;
-  void* ptrs[] = {d.clist, d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
+  void* ptrs[] = {d.clist, d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.brel, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
                   m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
   for (void* p : ptrs) if (p) Q(cudaFree(p));
   if (m->h_counters) Q(cudaFreeHost(m->h_counters));
@@ -307,7 +309,8 @@ static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls
   }
   if (mode == 0 || mode == 2) {
     k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip, n_dev);
-    m->launches++;
+    k_relocate_chains<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip, n_dev);
+    m->launches += 2;
   }
   CU(cudaGetLastError());
   if (!n_dev) m->has_root = true;
@@ -432,12 +435,14 @@ static int launch_knn(flb_map* m, KnnArgs a) {
     m->work_cap = cap;
   }
   a.worklist = m->worklist;
-  a.work_count = m->d_misc + 12;
   if (a.stride <= 0) a.stride = a.n;
-  CU(cudaMemsetAsync(a.work_count, 0, sizeof(int), m->stream));
+  if (!a.work_count) {   // (device-driven scans use per-pass counters zeroed by k_esikf_begin: no memset node per pass)
+    a.work_count = m->d_misc + 12;
+    CU(cudaMemsetAsync(a.work_count, 0, sizeof(int), m->stream));
+  }
   k_knn_stencil<K><<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
   // the fallback grid is sized for the typical <2 % unresolved share; it loops over the list
-  k_knn<K><<<m->sm_count * 4, 128, 0, m->stream>>>(a);
+  k_knn<K><<<m->sm_count * KNN_MIN_CTAS, KNN_THREADS, 0, m->stream>>>(a);   // all CTAs resident; they loop over the list
   m->launches += 2;
   return 0;
 }
@@ -468,7 +473,7 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
   a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt;
   a.max_d2 = (max_dist > 0.f && max_dist < 1e18f) ? max_dist * max_dist : INFINITY;
   a.phase_stats = nullptr;
-  a.ctl = nullptr; a.body = nullptr; a.stride = nq;
+  a.ctl = nullptr; a.body = nullptr; a.stride = nq; a.work_count = nullptr;
   int lrc = (K == 5) ? launch_knn<5>(m, a) : launch_knn<20>(m, a);
   cudaError_t le = lrc ? cudaErrorUnknown : cudaGetLastError();
   std::vector<float4> h((size_t)nq * K);
@@ -682,8 +687,9 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   s->cfg = *cfg;
   s->cap = cfg->max_scan_points;
   const size_t N = (size_t)s->cap;
-  s->res_grid = m->sm_count * 2;
-  cudaError_t e = cudaSuccess;
+  s->res_grid = m->sm_count;
+  cudaError_t e = cudaFuncSetAttribute(k_residual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, meas_smem_bytes<true>());   // > 48 KB
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_residual<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, meas_smem_bytes<false>());
   auto A = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); };
   A((void**)&s->body, sizeof(float4) * N);
   A((void**)&s->body_alt, sizeof(float4) * N);
@@ -892,14 +898,14 @@ static int enqueue_pass(flb_session* s, const double* state26, int search) {
     KnnArgs a;
     a.m = m->d; a.q = s->world; a.n = n; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
     a.phase_stats = m->prof_on ? m->d_phase : nullptr;
-    a.ctl = nullptr; a.body = nullptr; a.stride = s->cap;
+    a.ctl = nullptr; a.body = nullptr; a.stride = s->cap; a.work_count = nullptr;
     if (launch_knn<5>(m, a)) return 1;
   }
   const MeasArgs ma = meas_args(s, pose, search);
   {
     ProfScope ps(m, FLB_K_RESIDUAL);
-    if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
-    else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+    if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, meas_smem_bytes<true>(), st>>>(ma);
+    else k_residual<false><<<s->res_grid, MEAS_THREADS, meas_smem_bytes<false>(), st>>>(ma);
     m->launches++;
   }
   {
@@ -1036,19 +1042,22 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
   flb_map* m = s->map;
   cudaStream_t st = m->stream;
   const bool overlap = !m->prof_on;  // per-class event timing needs a single in-order stream
+  const bool md12 = s->cfg.extrinsic_est_en != 0;   // measured subspace: 12 columns with extrinsic estimation, else 6
   const int cap = s->cap;
   CU(cudaMemcpyAsync(s->d_x0P0, s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2), cudaMemcpyHostToDevice, st));
-  k_esikf_begin<<<1, 256, 0, st>>>(s->ctl, s->d_x0P0);
+  k_esikf_begin<<<1, 256, 0, st>>>(s->ctl, s->d_x0P0, m->d_misc + 16);
   m->launches++;
   for (int p = 0; p <= s->cfg.max_iterations; ++p) {
     if (overlap) {
       CU(cudaEventRecord(s->ev_fork[p], st));
       CU(cudaStreamWaitEvent(s->side, s->ev_fork[p], 0));
-      k_esikf_pre<<<1, dev::ESIKF_THREADS, 0, s->side>>>(s->ctl, s->d_scr);
+      if (md12) k_esikf_pre<12><<<1, dev::ESIKF_THREADS, 0, s->side>>>(s->ctl, s->d_scr);
+      else k_esikf_pre<6><<<1, dev::ESIKF_THREADS, 0, s->side>>>(s->ctl, s->d_scr);
       CU(cudaEventRecord(s->ev_join[p], s->side));
     } else {
       ProfScope ps(m, FLB_K_REDUCE);
-      k_esikf_pre<<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->d_scr);
+      if (md12) k_esikf_pre<12><<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->d_scr);
+      else k_esikf_pre<6><<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->d_scr);
     }
     m->launches++;
     {
@@ -1056,21 +1065,22 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
       KnnArgs a;
       a.m = m->d; a.q = nullptr; a.n = cap; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
       a.phase_stats = m->prof_on ? m->d_phase : nullptr;
-      a.ctl = s->ctl; a.body = s->body; a.stride = cap;
+      a.ctl = s->ctl; a.body = s->body; a.stride = cap; a.work_count = p < 8 ? m->d_misc + 16 + p : nullptr;
       if (launch_knn<5>(m, a)) return 1;
     }
     {
       ProfScope ps(m, FLB_K_RESIDUAL);
       MeasArgs ma = meas_args(s, PoseDev{}, 0);
       ma.ctl = s->ctl;
-      if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
-      else k_residual<false><<<s->res_grid, MEAS_THREADS, 0, st>>>(ma);
+      if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, meas_smem_bytes<true>(), st>>>(ma);
+      else k_residual<false><<<s->res_grid, MEAS_THREADS, meas_smem_bytes<false>(), st>>>(ma);
       m->launches++;
     }
     if (overlap) CU(cudaStreamWaitEvent(st, s->ev_join[p], 0));
     {
       ProfScope ps(m, FLB_K_REDUCE);
-      k_esikf_post<<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid, s->d_scr);
+      if (md12) k_esikf_post<12><<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid, s->d_scr);
+      else k_esikf_post<6><<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid, s->d_scr);
       m->launches++;
     }
   }
@@ -1368,3 +1378,23 @@ extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* bo
   if (flb_scan_step_begin(s, fov, body, n, stride, state26, P, flg_EKF_inited)) return 1;
   return flb_scan_step_finish(s, fov, state26, P, out);
 }
+
+#ifdef FLB_TRACE
+// Debug-library only (tools/trace_build.sh): read and reset the device-side timeline of trace.cuh.
+// out: TRACE_SLOTS x {t0, t1} global-timer ns (t0 = ~0 / t1 = 0 when the slot did not run); phases: TRACE_PHASES clock64 values.
+extern "C" int flb_debug_trace_read(unsigned long long* out, long long* phases, unsigned long long* dbg) {
+  std::vector<flb::TraceRec> h(flb::TRACE_SLOTS);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(h.data(), flb::g_trace, sizeof(flb::TraceRec) * flb::TRACE_SLOTS));
+  if (out) for (int i = 0; i < flb::TRACE_SLOTS; ++i) { out[2 * i] = h[i].t0; out[2 * i + 1] = h[i].t1; }
+  if (phases) CU(cudaMemcpyFromSymbol(phases, flb::g_phase_clk, sizeof(long long) * flb::TRACE_PHASES));
+  for (auto& r : h) { r.t0 = ~0ull; r.t1 = 0ull; }
+  CU(cudaMemcpyToSymbol(flb::g_trace, h.data(), sizeof(flb::TraceRec) * flb::TRACE_SLOTS));
+  if (dbg) CU(cudaMemcpyFromSymbol(dbg, flb::g_dbg, sizeof(unsigned long long) * flb::TRACE_DBG));
+  std::vector<unsigned long long> zd(flb::TRACE_DBG, 0);
+  CU(cudaMemcpyToSymbol(flb::g_dbg, zd.data(), sizeof(unsigned long long) * flb::TRACE_DBG));
+  std::vector<long long> z(flb::TRACE_PHASES, 0);
+  CU(cudaMemcpyToSymbol(flb::g_phase_clk, z.data(), sizeof(long long) * flb::TRACE_PHASES));
+  return 0;
+}
+#endif

@@ -19,6 +19,15 @@ namespace flb {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int BLOCK_RINGS = 3;  // block shells searched by the exact kernel before it falls back to the coarse levels
+// exact-kernel launch shape (threads per CTA, minimum CTAs per SM -> register cap)
+#ifndef FLB_KNN_THREADS
+#define FLB_KNN_THREADS 128
+#endif
+#ifndef FLB_KNN_MINB
+#define FLB_KNN_MINB 2
+#endif
+constexpr int KNN_THREADS = FLB_KNN_THREADS;
+constexpr int KNN_MIN_CTAS = FLB_KNN_MINB;
 
 template <int K>
 struct TopK {
@@ -59,42 +68,66 @@ __device__ __forceinline__ float sqdist(float qx, float qy, float qz, float px, 
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Merge the 32 lane-local sorted lists into the global top-K.  On return: lane r (< gcount) holds result r in
-// (rd,rx,ry,rz); every lane's list is cleared except lane r which re-inserts result r; returns gcount and the
-// current k-th distance (INF if fewer than K found) in thr.
+// Merge the lane-local sorted lists of the lanes in `gmask` (a whole warp, or an aligned group of G lanes working on
+// one query) into that query's top-K.  gl = lane index inside the group.  On return: group lane r (< gcount) holds
+// result r in (rd,rx,ry,rz); every lane's list is cleared except lane r which re-inserts result r; returns gcount and
+// the current k-th distance (INF if fewer than K found) in thr.  All lanes of gmask must call it together.
 template <int K>
-__device__ __forceinline__ int warp_merge(TopK<K>& t, int lane, float& rd, float& rx, float& ry, float& rz, float& thr) {
+__device__ __forceinline__ int warp_merge(TopK<K>& t, unsigned gmask, int gl, int lane, float& rd, float& rx, float& ry, float& rz,
+                                          float& thr) {
   int gcount = 0;
   float last = CUDART_INF_F;
   rd = CUDART_INF_F; rx = ry = rz = CUDART_NAN_F;
 #pragma unroll 1
-  for (int r = 0; r < K; ++r) {
+  for (int r = 0; r < K; ++r) {   // always K rounds (no early exit), so that lane groups sharing a warp stay converged
     const unsigned v = __float_as_uint(t.d[0]);
-    const unsigned mn = __reduce_min_sync(FULL, v);
-    if (mn == 0x7f800000u) break;
-    unsigned who = __ballot_sync(FULL, v == mn);
+    const unsigned mn = __reduce_min_sync(gmask, v);
+    const bool ok = mn != 0x7f800000u;   // group-uniform: a candidate is left
+    unsigned who = __ballot_sync(gmask, v == mn);
     int src = __ffs(who) - 1;
-    if (who & (who - 1)) {  // several lanes tie on distance: lexicographic (x,y,z)
-      float bx = __shfl_sync(FULL, t.x[0], src), by = __shfl_sync(FULL, t.y[0], src), bz = __shfl_sync(FULL, t.z[0], src);
+    if (ok && (who & (who - 1))) {  // several lanes tie on distance: lexicographic (x,y,z)
+      float bx = __shfl_sync(gmask, t.x[0], src), by = __shfl_sync(gmask, t.y[0], src), bz = __shfl_sync(gmask, t.z[0], src);
       unsigned rest = who & ~(1u << src);
       while (rest) {
         const int c = __ffs(rest) - 1;
         rest &= rest - 1;
-        const float cx = __shfl_sync(FULL, t.x[0], c), cy = __shfl_sync(FULL, t.y[0], c), cz = __shfl_sync(FULL, t.z[0], c);
+        const float cx = __shfl_sync(gmask, t.x[0], c), cy = __shfl_sync(gmask, t.y[0], c), cz = __shfl_sync(gmask, t.z[0], c);
         if (cx < bx || (cx == bx && (cy < by || (cy == by && cz < bz)))) { bx = cx; by = cy; bz = cz; src = c; }
       }
     }
-    const float gd = __shfl_sync(FULL, t.d[0], src), gx = __shfl_sync(FULL, t.x[0], src);
-    const float gy = __shfl_sync(FULL, t.y[0], src), gz = __shfl_sync(FULL, t.z[0], src);
-    if (lane == r) { rd = gd; rx = gx; ry = gy; rz = gz; }
-    if (lane == src) t.pop_front();
-    last = gd;
-    ++gcount;
+    const float gd = __shfl_sync(gmask, t.d[0], src), gx = __shfl_sync(gmask, t.x[0], src);
+    const float gy = __shfl_sync(gmask, t.y[0], src), gz = __shfl_sync(gmask, t.z[0], src);
+    if (ok) {
+      if (gl == r) { rd = gd; rx = gx; ry = gy; rz = gz; }
+      if (lane == src) t.pop_front();
+      last = gd;
+      ++gcount;
+    }
   }
   thr = (gcount == K) ? last : CUDART_INF_F;
   t.clear();
-  if (lane < gcount) { t.d[0] = rd; t.x[0] = rx; t.y[0] = ry; t.z[0] = rz; }
+  if (gl < gcount) { t.d[0] = rd; t.x[0] = rx; t.y[0] = ry; t.z[0] = rz; }
   return gcount;
+}
+
+// 64-bit voxel mask of a 4x4x4 block (slot order s = (z*4 + y)*4 + x) from three 4-bit per-axis masks
+__device__ __forceinline__ unsigned long long mask_from_axes(unsigned xm, unsigned ym, unsigned zm) {
+  const unsigned row = ((ym & 1u) ? xm : 0u) | ((ym & 2u) ? xm << 4 : 0u) | ((ym & 4u) ? xm << 8 : 0u) | ((ym & 8u) ? xm << 12 : 0u);
+  const unsigned lo = ((zm & 1u) ? row : 0u) | ((zm & 2u) ? row << 16 : 0u);
+  const unsigned hi = ((zm & 4u) ? row : 0u) | ((zm & 8u) ? row << 16 : 0u);
+  return ((unsigned long long)hi << 32) | lo;
+}
+// voxels of block (bx,by,bz) that lie inside the 5x5x5 stencil around voxel (cvx,cvy,cvz)
+__device__ __forceinline__ unsigned axis_in_stencil(int b, int cv) {
+  const int lo = cv - 2 - 4 * b, hi = cv + 2 - 4 * b;   // local coordinate range of the stencil in this block
+  if (hi < 0 || lo > 3) return 0u;
+  const int l = lo < 0 ? 0 : lo, h = hi > 3 ? 3 : hi;
+  return ((1u << (h - l + 1)) - 1u) << l;
+}
+__device__ __forceinline__ unsigned long long block_stencil_mask(int bx, int by, int bz, int cvx, int cvy, int cvz) {
+  const unsigned xm = axis_in_stencil(bx, cvx), ym = axis_in_stencil(by, cvy), zm = axis_in_stencil(bz, cvz);
+  if (!(xm && ym && zm)) return 0ull;
+  return mask_from_axes(xm, ym, zm);
 }
 
 // K0: body -> world transform (laserMapping.cpp:1894-1898): double math (Eigen quaternion * vector form), result
@@ -158,19 +191,6 @@ struct KnnArgs {
   int stride;          // leading dimension of nbr (>= n; the session capacity, so launches do not depend on n)
 };
 
-// visit every point of voxel slot `idx` (head + overflow chain)
-template <int K>
-__device__ __forceinline__ void visit_voxel(const MapDev& m, size_t idx, float qx, float qy, float qz, float lim, TopK<K>& t) {
-  float4 e = __ldg(&m.slots[idx]);
-  for (;;) {
-    const float dd = sqdist(qx, qy, qz, e.x, e.y, e.z);
-    if (dd <= lim) t.insert(dd, e.x, e.y, e.z);
-    const int c = __float_as_int(e.w);
-    if (c < 0) break;
-    e = __ldg(&m.ovf[c]);
-  }
-}
-
 // squared distance from q to the axis-aligned cell [lo,hi) per axis, shrunk by mg (conservative lower bound)
 __device__ __forceinline__ float box_mind2(float qx, float qy, float qz, float lx, float ly, float lz, float hx, float hy, float hz, float mg) {
   const float gx = fmaxf(fmaxf(lx - qx, qx - hx) - mg, 0.f);
@@ -185,31 +205,29 @@ __device__ __forceinline__ float cover2(float qx, float qy, float qz, float lx, 
 }
 
 // Scan the blocks flagged in `todo` (one candidate block per lane: its index `myblk`, occupancy `mymask` and block
-// coordinates) with the WHOLE warp: two blocks per step, lane l reads slots l and l+32 of each, so the 4 point loads of
+// coordinates) with the WHOLE warp: four blocks per step, lane l reads slots l and l+32 of each, so the 8 point loads of
 // a step are issued back to back (memory-level parallelism) before the insertions.  Voxels inside the phase-A
 // stencil (|v - cv| <= 2) were already visited and are skipped when skip_stencil is set.
 template <int K>
 __device__ __forceinline__ void coop_scan_blocks(const MapDev& m, unsigned todo, int myblk, unsigned long long mymask, int mybx,
                                                  int myby, int mybz, int lane, float qx, float qy, float qz, int cvx, int cvy,
                                                  int cvz, bool skip_stencil, float limit, TopK<K>& t) {
+  constexpr int NB = 4;
   while (todo) {
-    int src[2];
-    src[0] = __ffs(todo) - 1;
-    todo &= todo - 1;
-    src[1] = todo ? __ffs(todo) - 1 : -1;
-    if (src[1] >= 0) todo &= todo - 1;
-    float4 e[4];
-    bool v[4];
+    float4 e[2 * NB];
+    bool v[2 * NB];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int sl = src[u] >= 0 ? src[u] : 0;
+    for (int u = 0; u < NB; ++u) {
+      const int src = todo ? __ffs(todo) - 1 : -1;
+      todo &= todo - 1;   // (0 stays 0)
+      const int sl = src >= 0 ? src : 0;
       const int blk = __shfl_sync(FULL, myblk, sl);
       const unsigned long long mask = __shfl_sync(FULL, mymask, sl);
       const int bx = __shfl_sync(FULL, mybx, sl), by = __shfl_sync(FULL, myby, sl), bz = __shfl_sync(FULL, mybz, sl);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int s = lane + 32 * h;
-        bool ok = src[u] >= 0 && ((mask >> s) & 1ull);
+        bool ok = src >= 0 && ((mask >> s) & 1ull);
         if (ok && skip_stencil) {
           const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
           ok = !(abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2);
@@ -219,16 +237,15 @@ __device__ __forceinline__ void coop_scan_blocks(const MapDev& m, unsigned todo,
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2 * NB; ++j) {
       if (!v[j]) continue;
-      float4 p = e[j];
-      for (;;) {
-        const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
-        if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
-        const int c = __float_as_int(p.w);
-        if (c < 0) break;
-        p = __ldg(&m.ovf[c]);
-      }
+      const float4 p = e[j];
+      const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
+      if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
+      walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
+        const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+        if (d2 <= limit) t.insert(d2, o.x, o.y, o.z);
+      });
     }
   }
 }
@@ -273,155 +290,299 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
   }
 }
 
+// Scan the blocks flagged in `todo` (bit j: group lane j holds a candidate block: its index `myblk`, occupancy `mymask`
+// and packed block offset `myoff`) with the G lanes of one query group: two blocks per step, group lane gl owns the
+// slots gl, gl+G, ... of each block and keeps up to four independent 16-B point loads in flight.  Voxels inside the
+// 5x5x5 stencil were already visited by the stencil kernel and are masked out when skip_stencil is set.
+template <int K, int G>
+__device__ __forceinline__ void group_scan_blocks(const MapDev& m, unsigned gmask, int gbase, unsigned todo, int myblk,
+                                                  unsigned long long mymask, int myoff, int qbx, int qby, int qbz, int gl, float qx,
+                                                  float qy, float qz, int cvx, int cvy, int cvz, bool skip_stencil, float limit,
+                                                  TopK<K>& t) {
+  static_assert(G == 8 || G == 32, "group width");
+  const unsigned long long lanepat = (G == 32) ? ((1ull << gl) | (1ull << (gl + 32))) : (0x0101010101010101ull << gl);
+  // warp-uniform trip count (the groups of a warp run in lockstep; a group without work idles): divergent groups would
+  // be serialised by the hardware, which multiplies the latency of every query in the warp
+  while (__any_sync(FULL, todo != 0u)) {
+    unsigned long long c0 = 0ull, c1 = 0ull;
+    int b0 = 0, b1 = 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int src = todo ? __ffs(todo) - 1 : -1;
+      todo &= todo - 1;   // (0 stays 0)
+      const int sl = gbase + (src >= 0 ? src : 0);
+      const int blk = __shfl_sync(FULL, myblk, sl);
+      const unsigned long long mask = __shfl_sync(FULL, mymask, sl);
+      const int off = __shfl_sync(FULL, myoff, sl);
+      unsigned long long mm = src >= 0 ? (mask & lanepat) : 0ull;
+      if (skip_stencil && mm)
+        mm &= ~block_stencil_mask(qbx + (off & 15) - 8, qby + ((off >> 4) & 15) - 8, qbz + (off >> 8) - 8, cvx, cvy, cvz);
+      if (u == 0) { c0 = mm; b0 = blk; } else { c1 = mm; b1 = blk; }
+    }
+    for (;;) {   // per-lane candidate loop (ordinary SIMT masking: lanes drop out as they run dry)
+      unsigned pid[4];
+      int nc = 0;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        pid[v] = 0u;
+        if (c0) { pid[v] = (unsigned)b0 * 64u + (unsigned)(__ffsll((long long)c0) - 1); c0 &= c0 - 1; nc = v + 1; }
+        else if (c1) { pid[v] = (unsigned)b1 * 64u + (unsigned)(__ffsll((long long)c1) - 1); c1 &= c1 - 1; nc = v + 1; }
+      }
+      if (nc == 0) break;
+      float4 e[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (v < nc) e[v] = __ldg(&m.slots[pid[v]]);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (v < nc) {
+          const float4 p = e[v];
+          const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
+          if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
+          walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
+            const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+            if (d2 <= limit) t.insert(d2, o.x, o.y, o.z);
+          });
+        }
+      }
+      if (nc < 4) break;
+    }
+  }
+}
+
+// Finish ONE query with the whole warp over the coarse levels (rare: map frontier).  A real call (noinline) so that its
+// register needs do not inflate the group kernel; wcount/wthr/seed = state of the query after the block rings (lane r
+// passes result r in sd,sx,sy,sz).
 template <int K>
-__global__ void __launch_bounds__(128) k_knn(KnnArgs a) {
+__device__ __noinline__ void warp_finish_coarse(MapDev m, float4* nbr, unsigned char* cnt, int* phase_stats, int stride, float lim,
+                                                int qi, float wqx, float wqy, float wqz, int wcount, float wthr, float sd, float sx,
+                                                float sy, float sz) {
+  const int lane = threadIdx.x & 31;
+  const float ds = m.ds;
+    TopK<K> tw;
+    tw.clear();
+    float wd_ = CUDART_INF_F, wx = CUDART_NAN_F, wy = CUDART_NAN_F, wz = CUDART_NAN_F;
+    if (lane < wcount) { wd_ = sd; wx = sx; wy = sy; wz = sz; tw.d[0] = sd; tw.x[0] = sx; tw.y[0] = sy; tw.z[0] = sz; }
+    const int cvx = voxel_of(wqx, ds), cvy = voxel_of(wqy, ds), cvz = voxel_of(wqz, ds);
+    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(wqx) + fabsf(wqy) + fabsf(wqz));
+    const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+    int phase = 2;
+    {
+      // ---------------- phase B: 3x3x3 coarse cells around the query
+      const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
+      int mycs = -1;
+      if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
+      // nearest cells first (centre cell), so the bound tightens early
+      const unsigned present = __ballot_sync(FULL, mycs >= 0);
+      {
+        const int cs = __shfl_sync(FULL, mycs, 13);
+        if (cs >= 0) scan_coarse_cell<K>(m, cs, lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+        if (wcount < K) wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);  // get a finite bound before the ring
+      }
+      unsigned rest = present & ~(1u << 13);
+      while (rest) {
+        const int c = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int cs = __shfl_sync(FULL, mycs, c);
+        scan_coarse_cell<K>(m, cs, lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+      }
+      wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
+      const float cs32 = 32.f * ds;
+      const float cov = cover2(wqx, wqy, wqz, (float)(qcx - 1) * cs32, (float)(qcy - 1) * cs32, (float)(qcz - 1) * cs32,
+                               (float)(qcx + 2) * cs32, (float)(qcy + 2) * cs32, (float)(qcz + 2) * cs32, mg);
+      const bool wdone = (wcount == K && wthr < cov) || cov > lim;
+      if (!wdone) {
+        // ---------------- phase C: exhaustive scan of the coarse hash with box-distance pruning
+        phase = 3;
+        const int ncs = m.counters[CNT_COARSE_USED];   // dense list of occupied coarse cells
+#pragma unroll 1
+        for (int base = 0; base < ncs; base += 32) {
+          const int li = base + lane;
+          const int cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
+          const uint64_t ck = cs >= 0 ? __ldg(&m.ckeys[cs]) : KEY_EMPTY;
+          bool go = false;
+          if (ck != KEY_EMPTY) {
+            int cx, cy, cz;
+            unpack_key(ck, cx, cy, cz);
+            if (!(abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1)) {
+              const float md = box_mind2(wqx, wqy, wqz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32,
+                                         (float)(cx + 1) * cs32, (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
+              go = (wcount < K || md <= wthr) && md <= lim;
+            }
+          }
+          unsigned todo = __ballot_sync(FULL, go);
+          if (!todo) continue;
+          while (todo) {
+            const int c = __ffs(todo) - 1;
+            todo &= todo - 1;
+            scan_coarse_cell<K>(m, __shfl_sync(FULL, cs, c), lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+          }
+          wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
+        }
+      }
+    }
+    if (lane < K) nbr[(size_t)lane * stride + qi] = make_float4(wx, wy, wz, wd_);
+    if (lane == 0) {
+      cnt[qi] = (unsigned char)wcount;
+      if (phase_stats) atomicAdd(&phase_stats[phase], 1);
+    }
+}
+
+// K1b: exact completion of the queries the stencil kernel could not prove complete (its work list).  The stencil
+// kernel has already visited the whole 5x5x5 voxel stencil and left its (up to K) best points in the neighbour cache:
+// they seed the search, which then only looks OUTSIDE the stencil.
+//   * shells of BLOCKS around the query block, radius 1..BLOCK_RINGS, are searched by a GROUP of G lanes per query
+//     (G = 8 for K <= 8: four queries per warp, so a few thousand unresolved queries are all in flight at once — the
+//     kernel is a chain of dependent DRAM/L2 round trips per query, i.e. bound by queries in flight x latency);
+//   * the rare query still unresolved after ring 3 (2.4 m at 0.2 m voxels; map frontier) is finished by the WHOLE warp
+//     over the coarse levels: 3x3x3 coarse cells, then every remaining coarse cell with box-distance pruning.
+template <int K>
+__global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
+  constexpr int G = (K <= 8) ? 8 : 32;   // lanes per query (group lane r must be able to hold result r: G >= K)
+  constexpr int QPW = 32 / G;            // queries per warp
   const MapDev& m = a.m;
   const int lane = threadIdx.x & 31;
+  const int g = lane / G, gl = lane - g * G, gbase = g * G;
+  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << gbase);
+  const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   const float ds = m.ds;
   const float lim = a.max_d2;
+  FLB_TRACE_BEGIN(3 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
-  const int nwork = a.worklist ? *a.work_count : a.n;
-  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwork; w += warps_per_grid) {
-    const int i = a.worklist ? a.worklist[w] : w;
-    const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
-    const float qx = q4.x, qy = q4.y, qz = q4.z;
+  const int nwork = *a.work_count;
+  for (int wb = warp_id * QPW; wb < nwork; wb += warps_per_grid * QPW) {   // warp-uniform trip count
+    const int w = wb + g;
+    const bool active = w < nwork;
+    int i = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
     TopK<K> t;
     t.clear();
     float rd = CUDART_INF_F, rx = CUDART_NAN_F, ry = CUDART_NAN_F, rz = CUDART_NAN_F, thr = CUDART_INF_F;
     int gcount = 0;
-    int phase = 0;
-    const float qlim = 4.0e6f * ds;
-    const bool qok = fabsf(qx) < qlim && fabsf(qy) < qlim && fabsf(qz) < qlim;
-    if (qok) {
-      const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
-      const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
-      // ---------------- phase A: 5x5x5 stencil, inside the 2x2x2 blocks starting at bb
-      const int bbx = (cvx - 2) >> 2, bby = (cvy - 2) >> 2, bbz = (cvz - 2) >> 2;
-      int myblk = -1;
-      unsigned long long mymask = 0ull;
-      if (lane < 8) {
-        myblk = find_block(m, pack_key(bbx + (lane & 1), bby + ((lane >> 1) & 1), bbz + (lane >> 2)));
-        if (myblk >= 0) mymask = __ldg(&m.bmask[myblk]);
+    bool done = true;
+    FLB_DBG_CLOCK(e0);
+    int dbg_rings = 0;
+    (void)dbg_rings;
+    int cvx = 0, cvy = 0, cvz = 0;
+    float mg = 0.f;
+    if (active) {
+      i = a.worklist[w];
+      const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
+      qx = q4.x; qy = q4.y; qz = q4.z;
+      // ---------------- seed: the stencil kernel's result (state as after a merge: group lane r holds result r)
+      gcount = a.cnt[i];
+      if (gl < gcount) {
+        const float4 sd = a.nbr[(size_t)gl * a.stride + i];   // plain load: written by the preceding kernel
+        rd = sd.w; rx = sd.x; ry = sd.y; rz = sd.z;
+        t.d[0] = rd; t.x[0] = rx; t.y[0] = ry; t.z[0] = rz;
       }
+      done = false;
+      cvx = voxel_of(qx, ds); cvy = voxel_of(qy, ds); cvz = voxel_of(qz, ds);
+      mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+    }
+    {
+      const float dk = __shfl_sync(FULL, rd, gbase + K - 1);
+      thr = gcount == K ? dk : CUDART_INF_F;
+    }
+    const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+    const float bs4 = 4.f * ds;
+    // ---------------- shells of blocks, radius 1..BLOCK_RINGS.  ALL control flow below is warp-uniform (groups that are
+    // finished idle under predicates): groups on divergent paths would be serialised.  Up to four shell blocks per lane
+    // and round: their hash probes (and then their occupancy words) are independent loads issued back to back.  Ring r
+    // covers >= 4r voxels around the query; ring 3 exceeds the 5 m^2 acceptance radius of h_share_model.
+#pragma unroll 1
+    for (int r = 1; r <= BLOCK_RINGS; ++r) {
+      if (!__any_sync(FULL, !done)) break;
+      const bool go = !done;
+      const int wd = 2 * r + 1, nb = wd * wd * wd;
+      const float bound = gcount == K ? thr : CUDART_INF_F;
+#pragma unroll 1
+      for (int base = 0; base < nb; base += 4 * G) {
+        int off[4], blk[4];   // off: packed block offsets (dx+8) | (dy+8) << 4 | (dz+8) << 8, -1 = no probe
+        uint4 ent[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int v = lane + 32 * r;
-        const bool act = v < 125;
-        const int vv = act ? v : 0;
-        const int vx = cvx + (vv % 5) - 2, vy = cvy + ((vv / 5) % 5) - 2, vz = cvz + (vv / 25) - 2;
-        const int bsel = ((vx >> 2) - bbx) + 2 * ((vy >> 2) - bby) + 4 * ((vz >> 2) - bbz);
-        const int blk = __shfl_sync(FULL, myblk, bsel);
-        const unsigned long long mask = __shfl_sync(FULL, mymask, bsel);
-        const int s = (((vz & 3) << 2) + (vy & 3)) * 4 + (vx & 3);
-        if (act && blk >= 0 && ((mask >> s) & 1ull)) visit_voxel<K>(m, (size_t)blk * 64 + s, qx, qy, qz, lim, t);
-      }
-      gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
-      float cov = cover2(qx, qy, qz, (float)(cvx - 2) * ds, (float)(cvy - 2) * ds, (float)(cvz - 2) * ds,
-                         (float)(cvx + 3) * ds, (float)(cvy + 3) * ds, (float)(cvz + 3) * ds, mg);
-      bool done = (gcount == K && thr < cov) || cov > lim;
-      const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
-      if (!done) {
-        // ---------------- phase B0: shells of BLOCKS around the query block, radius 1..BLOCK_RINGS (one shell block per
-        // lane and round, hash probes in parallel, candidates scanned co-operatively).  Ring r covers >= 4r voxels around
-        // the query; ring 3 (2.4 m at 0.2 m voxels) exceeds the 5 m^2 acceptance radius of h_share_model, so only
-        // genuinely far queries (map frontier) go on to the coarse levels.
-        phase = 1;
-        const float bs4 = 4.f * ds;
-#pragma unroll 1
-        for (int r = 1; r <= BLOCK_RINGS && !done; ++r) {
-          const int w = 2 * r + 1, nb = w * w * w;
-          const float bound = gcount == K ? thr : CUDART_INF_F;
-#pragma unroll 1
-          for (int base = 0; base < nb; base += 32) {
-            const int idx = base + lane;
-            int bx = 0, by = 0, bz = 0, blk = -1;
-            unsigned long long mask = 0ull;
-            if (idx < nb) {
-              const int dx = idx % w - r, dy = (idx / w) % w - r, dz = idx / (w * w) - r;
-              // shell only — the interior was visited by smaller rings; ring 1 also takes the query's own block, whose
-              // voxels outside the 5x5x5 stencil have not been seen yet
-              if (r == 1 || max(abs(dx), max(abs(dy), abs(dz))) == r) {
-                bx = qbx + dx; by = qby + dy; bz = qbz + dz;
-                const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
-                const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);
-                if (!(md > bound || md > lim)) {
-                  blk = find_block(m, pack_key(bx, by, bz));
-                  if (blk >= 0) mask = __ldg(&m.bmask[blk]);
-                }
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + G * u + gl;
+          off[u] = -1;
+          if (go && idx < nb) {
+            const int dx = idx % wd - r, dy = (idx / wd) % wd - r, dz = idx / (wd * wd) - r;
+            // shell only — the interior was visited by smaller rings; ring 1 also takes the query's own block, whose
+            // voxels outside the 5x5x5 stencil have not been seen yet
+            if (r == 1 || max(abs(dx), max(abs(dy), abs(dz))) == r) {
+              const int bx = qbx + dx, by = qby + dy, bz = qbz + dz;
+              const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
+              const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);
+              if (!(md > bound || md > lim)) {
+                off[u] = (dx + 8) | ((dy + 8) << 4) | ((dz + 8) << 8);
+                ent[u] = __ldg(reinterpret_cast<const uint4*>(&m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask]));
               }
             }
-            const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
-            if (todo) coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, r == 1, fminf(lim, bound), t);
           }
-          gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
-          cov = cover2(qx, qy, qz, (float)(qbx - r) * bs4, (float)(qby - r) * bs4, (float)(qbz - r) * bs4,
-                       (float)(qbx + r + 1) * bs4, (float)(qby + r + 1) * bs4, (float)(qbz + r + 1) * bs4, mg);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          blk[u] = -1;
+          if (off[u] >= 0) {
+            const uint64_t key = pack_key(qbx + (off[u] & 15) - 8, qby + ((off[u] >> 4) & 15) - 8, qbz + (off[u] >> 8) - 8);
+            const uint64_t k0 = ((uint64_t)ent[u].y << 32) | ent[u].x;
+            blk[u] = (k0 == key) ? (int)ent[u].z : (k0 == KEY_EMPTY ? -1 : find_block(m, key));
+          }
+        }
+        unsigned long long mask[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mask[u] = blk[u] >= 0 ? __ldg(&m.bmask[blk[u]]) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned bal = __ballot_sync(FULL, blk[u] >= 0 && mask[u] != 0ull);
+          const unsigned todo = (G == 32) ? bal : ((bal >> gbase) & ((1u << G) - 1u));
+          group_scan_blocks<K, G>(m, gmask, gbase, todo, blk[u], mask[u], off[u], qbx, qby, qbz, gl, qx, qy, qz, cvx, cvy, cvz,
+                                  r == 1, fminf(lim, bound), t);
+        }
+      }
+      {
+        // merge (all groups together; for a finished group it reproduces its result)
+        const int gc = warp_merge<K>(t, gmask, gl, lane, rd, rx, ry, rz, thr);
+        if (go) {
+          gcount = gc;
+          dbg_rings = r;
+          const float cov = cover2(qx, qy, qz, (float)(qbx - r) * bs4, (float)(qby - r) * bs4, (float)(qbz - r) * bs4,
+                                   (float)(qbx + r + 1) * bs4, (float)(qby + r + 1) * bs4, (float)(qbz + r + 1) * bs4, mg);
           done = (gcount == K && thr < cov) || cov > lim;
         }
       }
-      if (!done) {
-        // ---------------- phase B: 3x3x3 coarse cells around the query (blocks of B0 are skipped inside)
-        phase = 2;
-        const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
-        int mycs = -1;
-        if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
-        // nearest cells first (centre cell), so the bound tightens early
-        const unsigned present = __ballot_sync(FULL, mycs >= 0);
-        {
-          const int cs = __shfl_sync(FULL, mycs, 13);
-          if (cs >= 0) scan_coarse_cell<K>(m, cs, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
-          if (gcount < K) gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);  // get a finite bound before the ring
-        }
-        unsigned rest = present & ~(1u << 13);
-        while (rest) {
-          const int c = __ffs(rest) - 1;
-          rest &= rest - 1;
-          const int cs = __shfl_sync(FULL, mycs, c);
-          scan_coarse_cell<K>(m, cs, lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
-        }
-        gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
-        const float cs32 = 32.f * ds;
-        cov = cover2(qx, qy, qz, (float)(qcx - 1) * cs32, (float)(qcy - 1) * cs32, (float)(qcz - 1) * cs32,
-                     (float)(qcx + 2) * cs32, (float)(qcy + 2) * cs32, (float)(qcz + 2) * cs32, mg);
-        done = (gcount == K && thr < cov) || cov > lim;
-        if (!done) {
-          // ---------------- phase C: exhaustive scan of the coarse hash with box-distance pruning
-          phase = 3;
-          const int ncs = m.counters[CNT_COARSE_USED];   // dense list of occupied coarse cells
-#pragma unroll 1
-          for (int base = 0; base < ncs; base += 32) {
-            const int li = base + lane;
-            const int cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
-            const uint64_t ck = cs >= 0 ? __ldg(&m.ckeys[cs]) : KEY_EMPTY;
-            bool go = false;
-            if (ck != KEY_EMPTY) {
-              int cx, cy, cz;
-              unpack_key(ck, cx, cy, cz);
-              if (!(abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1)) {
-                const float md = box_mind2(qx, qy, qz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32,
-                                           (float)(cx + 1) * cs32, (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
-                go = (gcount < K || md <= thr) && md <= lim;
-              }
-            }
-            unsigned todo = __ballot_sync(FULL, go);
-            if (!todo) continue;
-            while (todo) {
-              const int c = __ffs(todo) - 1;
-              todo &= todo - 1;
-              scan_coarse_cell<K>(m, __shfl_sync(FULL, cs, c), lane, qx, qy, qz, cvx, cvy, cvz, gcount == K, thr, lim, mg, t);
-            }
-            gcount = warp_merge<K>(t, lane, rd, rx, ry, rz, thr);
-          }
-        }
+    }
+    if (active && done) {
+      if (gl < K) a.nbr[(size_t)gl * a.stride + i] = make_float4(rx, ry, rz, rd);
+      if (gl == 0) {
+        a.cnt[i] = (unsigned char)gcount;
+        if (a.phase_stats) atomicAdd(&a.phase_stats[1], 1);
       }
     }
-    if (lane < K) a.nbr[(size_t)lane * a.stride + i] = make_float4(rx, ry, rz, rd);
-    if (lane == 0) {
-      a.cnt[i] = (unsigned char)gcount;
-      if (a.phase_stats) atomicAdd(&a.phase_stats[phase], 1);
+#ifdef FLB_TRACE
+    if (active && gl == 0 && a.ctl && a.ctl->it == -1) {
+      const long long e1 = clock64();
+      FLB_DBG_ADD(16, 1); FLB_DBG_ADD(17, e1 - e0); FLB_DBG_MAX(18, e1 - e0); FLB_DBG_ADD(18 + dbg_rings, 1);
+      FLB_DBG_ADD(25, done ? 0 : 1);
+    }
+#endif
+    // ---------------- queries still unresolved after the block rings: the WHOLE warp finishes them one at a time over
+    // the coarse levels (the blocks of the rings are skipped inside scan_coarse_cell)
+    __syncwarp();
+    unsigned pend = __ballot_sync(FULL, active && !done && gl == 0);
+    while (pend) {
+      const int src = __ffs(pend) - 1;   // leader lane of the unresolved group
+      pend &= pend - 1;
+      const int qi = __shfl_sync(FULL, i, src);
+      const float wqx = __shfl_sync(FULL, qx, src), wqy = __shfl_sync(FULL, qy, src), wqz = __shfl_sync(FULL, qz, src);
+      int wcount = __shfl_sync(FULL, gcount, src);
+      float wthr = __shfl_sync(FULL, thr, src);
+      const int sl = src + (lane < K ? lane : 0);   // result r of that query lives in its group lane r
+      const float sd = __shfl_sync(FULL, rd, sl), sx = __shfl_sync(FULL, rx, sl), sy = __shfl_sync(FULL, ry, sl), sz = __shfl_sync(FULL, rz, sl);
+      warp_finish_coarse<K>(m, a.nbr, a.cnt, a.phase_stats, a.stride, lim, qi, wqx, wqy, wqz, wcount, wthr, sd, sx, sy, sz);
     }
   }
+  FLB_TRACE_END(3 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
 }
 
 // K1a: phase A with ONE THREAD per query (the common case: >99 % of LiDAR returns lie on mapped surfaces and are
@@ -455,15 +616,29 @@ struct TopKId {
 };
 
 constexpr int STENCIL_THREADS = 128;
+constexpr int SHELL_LIST = 32;   // per-thread capacity of the surviving-shell-voxel list (bytes of shared memory)
 
-// One pass over the candidate voxels recorded in s_cand (per-thread smem column).  PRUNE: skip a voxel (head load and
-// overflow chain) when the squared distance from the query to the voxel's box — a lower bound for every point keyed
-// to that voxel, looked up from per-axis gap tables — already exceeds the current k-th distance.
-template <int K, bool PRUNE>
-__device__ __forceinline__ void stencil_pass(const MapDev& m, const int (*s_blk)[STENCIL_THREADS],
-                                             const unsigned long long (*s_cand)[STENCIL_THREADS],
-                                             const float (*s_gap)[STENCIL_THREADS], int tid, int ox, int oy, int oz, float qx, float qy,
-                                             float qz, float lim, TopKId<K>& t, int& n_head, int& n_chain) {
+// Occupancy-independent part of the candidate masks.  ax/ay/az are 8-bit per-axis masks over the 2 blocks the stencil
+// spans (bits 0..3: local coordinates of the low block, 4..7: of the high block); the result is the 64-bit voxel mask
+// of block half b (bit 0: x half, 1: y half, 2: z half) in slot order s = (z*4 + y)*4 + x.
+__device__ __forceinline__ unsigned long long stencil_mask(unsigned ax, unsigned ay, unsigned az, int b) {
+  return mask_from_axes((ax >> ((b & 1) << 2)) & 15u, (ay >> (((b >> 1) & 1) << 2)) & 15u, (az >> ((b >> 2) << 2)) & 15u);
+}
+
+// Per-thread shared-memory columns of the stencil kernel: 188 B per query, so that 7 CTAs of 128 threads (the register
+// limit) fit one SM and a 120k-point scan is a single wave on 148 SMs.
+struct StencilSmem {
+  int blk[8][STENCIL_THREADS];                     // block index of the 8 probed blocks (-1: absent)
+  unsigned long long c5[8][STENCIL_THREADS];       // occupied voxels of each block inside the 5x5x5 stencil
+  float gap[15][STENCIL_THREADS];                  // squared query-to-slab gaps: x[5], y[5], z[5]
+  unsigned char list[SHELL_LIST][STENCIL_THREADS]; // surviving shell voxels, stencil-relative index jx + 5 jy + 25 jz
+};
+
+// Visit the candidate voxels (c5 & inner mask, or c5 & ~inner mask when OUTER) of the 8 blocks: per-thread cursor over
+// the blocks, four independent 16-B point loads in flight, branch-free insertion.
+template <int K, bool OUTER>
+__device__ __forceinline__ void stencil_pass(const MapDev& m, const StencilSmem& sm, int tid, unsigned ix, unsigned iy, unsigned iz,
+                                             float qx, float qy, float qz, float lim, TopKId<K>& t, int& n_head, int& n_chain) {
   int b = -1, blk = 0;
   unsigned long long cand = 0ull;
   for (;;) {
@@ -472,20 +647,17 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const int (*s_blk)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       pid[u] = 0u;
-      for (;;) {
-        while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; blk = s_blk[b][tid]; }
-        if (cand == 0ull) break;
+      while (cand == 0ull && b < 7) {
+        ++b;
+        const unsigned long long in3 = stencil_mask(ix, iy, iz, b);
+        cand = sm.c5[b][tid] & (OUTER ? ~in3 : in3);
+        blk = sm.blk[b][tid];
+      }
+      if (cand != 0ull) {
         const int sl = __ffsll((long long)cand) - 1;
         cand &= cand - 1;
-        if (PRUNE) {
-          // stencil-relative voxel index per axis (0..4): block half (bit of b) * 4 + local coordinate - stencil origin
-          const int jx = ((b & 1) << 2) + (sl & 3) - ox, jy = (((b >> 1) & 1) << 2) + ((sl >> 2) & 3) - oy, jz = ((b >> 2) << 2) + (sl >> 4) - oz;
-          const float md = s_gap[jx][tid] + s_gap[5 + jy][tid] + s_gap[10 + jz][tid];
-          if (md > t.d[K - 1]) continue;  // no point of this voxel can enter the top-K
-        }
         pid[u] = (unsigned)blk * 64u + (unsigned)sl;
         nc = u + 1;
-        break;
       }
     }
     if (nc == 0) break;
@@ -499,14 +671,11 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const int (*s_blk)
         float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
         if (dd <= lim) t.insert(dd, pid[u]);
         ++n_head;
-        int c = __float_as_int(e[u].w);
-        while (c >= 0) {  // overflow chain of this voxel
+        walk_chain(m, __float_as_int(e[u].w), [&](const float4 o, int c) {  // overflow chain of this voxel
           ++n_chain;
-          const float4 o = __ldg(&m.ovf[c]);
-          dd = sqdist(qx, qy, qz, o.x, o.y, o.z);
-          if (dd <= lim) t.insert(dd, 0x80000000u | (unsigned)c);
-          c = __float_as_int(o.w);
-        }
+          const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+          if (d2 <= lim) t.insert(d2, 0x80000000u | (unsigned)c);
+        });
       }
     }
     if (nc < 4) break;
@@ -516,13 +685,10 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const int (*s_blk)
 // Outer-shell pass: (1) a flat, load-free loop tests every occupied shell voxel against the k-th distance known after
 // the inner pass (box lower bound from the per-axis gap tables) and compacts the survivors into a small per-thread list
 // — lanes only diverge on cheap code; (2) the survivors are loaded four at a time.  Returns false if the list overflowed
-// (the query then goes to the exact kernel).
-constexpr int SHELL_LIST = 32;
+// (the caller then visits the whole shell).
 template <int K>
-__device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, const int (*s_blk)[STENCIL_THREADS],
-                                                   const unsigned long long (*s_cand)[STENCIL_THREADS],
-                                                   const float (*s_gap)[STENCIL_THREADS], unsigned short (*s_list)[STENCIL_THREADS],
-                                                   int tid, int ox, int oy, int oz, float qx, float qy, float qz, float lim,
+__device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem& sm, int tid, unsigned ix, unsigned iy, unsigned iz,
+                                                   int ox, int oy, int oz, float qx, float qy, float qz, float lim,
                                                    TopKId<K>& t, int& n_head, int& n_chain) {
   const float bound = t.d[K - 1];
   int ns = 0;
@@ -530,14 +696,15 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, const int (*
     int b = -1;
     unsigned long long cand = 0ull;
     for (;;) {
-      while (cand == 0ull && b < 7) { ++b; cand = s_cand[b][tid]; }
+      while (cand == 0ull && b < 7) { ++b; cand = sm.c5[b][tid] & ~stencil_mask(ix, iy, iz, b); }
       if (cand == 0ull) break;
       const int sl = __ffsll((long long)cand) - 1;
       cand &= cand - 1;
+      // stencil-relative voxel index per axis (0..4): block half * 4 + local coordinate - stencil origin
       const int jx = ((b & 1) << 2) + (sl & 3) - ox, jy = (((b >> 1) & 1) << 2) + ((sl >> 2) & 3) - oy, jz = ((b >> 2) << 2) + (sl >> 4) - oz;
-      const float md = s_gap[jx][tid] + s_gap[5 + jy][tid] + s_gap[10 + jz][tid];
+      const float md = sm.gap[jx][tid] + sm.gap[5 + jy][tid] + sm.gap[10 + jz][tid];
       if (!(md > bound)) {  // a point of this voxel could still enter the top-K
-        if (ns < SHELL_LIST) s_list[ns][tid] = (unsigned short)((b << 6) | sl);
+        if (ns < SHELL_LIST) sm.list[ns][tid] = (unsigned char)(jx + 5 * jy + 25 * jz);
         ++ns;
       }
     }
@@ -550,8 +717,11 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, const int (*
     for (int u = 0; u < 4; ++u) {
       pid[u] = 0u;
       if (base + u < ns) {
-        const unsigned v = s_list[base + u][tid];
-        pid[u] = (unsigned)s_blk[v >> 6][tid] * 64u + (v & 63u);
+        const int j = sm.list[base + u][tid];
+        const int jz = j / 25, r = j - 25 * jz, jy = r / 5, jx = r - 5 * jy;
+        const int vx = ox + jx, vy = oy + jy, vz = oz + jz;   // 0..7 across the two blocks per axis
+        const int b = (vx >> 2) | ((vy >> 2) << 1) | ((vz >> 2) << 2);
+        pid[u] = (unsigned)sm.blk[b][tid] * 64u + (unsigned)((vx & 3) | ((vy & 3) << 2) | ((vz & 3) << 4));
         e[u] = __ldg(&m.slots[pid[u]]);
       }
     }
@@ -561,14 +731,11 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, const int (*
         float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
         if (dd <= lim) t.insert(dd, pid[u]);
         ++n_head;
-        int c = __float_as_int(e[u].w);
-        while (c >= 0) {  // overflow chain of this voxel
+        walk_chain(m, __float_as_int(e[u].w), [&](const float4 o, int c) {  // overflow chain of this voxel
           ++n_chain;
-          const float4 o = __ldg(&m.ovf[c]);
-          dd = sqdist(qx, qy, qz, o.x, o.y, o.z);
-          if (dd <= lim) t.insert(dd, 0x80000000u | (unsigned)c);
-          c = __float_as_int(o.w);
-        }
+          const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+          if (d2 <= lim) t.insert(d2, 0x80000000u | (unsigned)c);
+        });
       }
     }
   }
@@ -577,14 +744,11 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, const int (*
 
 template <int K>
 __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
-  __shared__ int s_blk[8][STENCIL_THREADS];
-  __shared__ unsigned long long s_cand1[8][STENCIL_THREADS];   // occupied voxels of the inner 3x3x3
-  __shared__ unsigned long long s_cand2[8][STENCIL_THREADS];   // occupied voxels of the outer shell of the 5x5x5
-  __shared__ float s_gap[15][STENCIL_THREADS];                 // squared query-to-slab gaps: x[5], y[5], z[5]
-  __shared__ unsigned short s_list[SHELL_LIST][STENCIL_THREADS];  // surviving shell voxels (block half << 6 | slot)
+  __shared__ StencilSmem sm;
   const MapDev& m = a.m;
   const int tid = threadIdx.x;
   const int i = blockIdx.x * blockDim.x + tid;
+  FLB_TRACE_BEGIN(2 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
   if (i >= (a.ctl ? a.ctl->n : a.n)) return;
   const float ds = m.ds;
@@ -602,17 +766,8 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     // per axis the 5-wide stencil covers local range [o,3] of the low block and [0,o] of the high block; the inner
     // 3-wide one is the same shifted by one voxel
     const int ox = (cvx - 2) & 3, oy = (cvy - 2) & 3, oz = (cvz - 2) & 3;
-    unsigned x5[2], y5[2], z5[2], x3[2], y3[2], z3[2];
-    {
-      const unsigned mx5 = 31u << ox, my5 = 31u << oy, mz5 = 31u << oz, mx3 = 14u << ox, my3 = 14u << oy, mz3 = 14u << oz;
-      x5[0] = mx5 & 15u; x5[1] = (mx5 >> 4) & 15u; y5[0] = my5 & 15u; y5[1] = (my5 >> 4) & 15u; z5[0] = mz5 & 15u; z5[1] = (mz5 >> 4) & 15u;
-      x3[0] = mx3 & 15u; x3[1] = (mx3 >> 4) & 15u; y3[0] = my3 & 15u; y3[1] = (my3 >> 4) & 15u; z3[0] = mz3 & 15u; z3[1] = (mz3 >> 4) & 15u;
-    }
-    auto spread_y = [](unsigned ym) { return (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9); };  // bits 0,4,8,12
-    auto spread_z = [](unsigned zm) {
-      return (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) | ((unsigned long long)(zm & 4u) << 30) |
-             ((unsigned long long)(zm & 8u) << 45);                                                                      // bits 0,16,32,48
-    };
+    const unsigned ax5 = 31u << ox, ay5 = 31u << oy, az5 = 31u << oz;   // 5-wide axis masks over the two blocks
+    const unsigned ix = 14u << ox, iy = 14u << oy, iz = 14u << oz;      // inner 3-wide axis masks
     // squared gaps from the query to the 5 voxel slabs per axis (conservative: shrunk by the rounding margin)
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -620,9 +775,9 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
       const float gx = fmaxf(fmaxf(lx - qx, qx - (lx + ds)) - mg, 0.f);
       const float gy = fmaxf(fmaxf(ly - qy, qy - (ly + ds)) - mg, 0.f);
       const float gz = fmaxf(fmaxf(lz - qz, qz - (lz + ds)) - mg, 0.f);
-      s_gap[j][tid] = gx * gx;
-      s_gap[5 + j][tid] = gy * gy;
-      s_gap[10 + j][tid] = gz * gz;
+      sm.gap[j][tid] = gx * gx;
+      sm.gap[5 + j][tid] = gy * gy;
+      sm.gap[10 + j][tid] = gz * gz;
     }
     // ---- the 8 hash probes are INDEPENDENT loads: issue them back to back (memory-level parallelism), then resolve;
     // only a collision (first slot holds another key) falls back to the sequential probe loop
@@ -644,18 +799,14 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     for (int b = 0; b < 8; ++b) occ[b] = blk8[b] >= 0 ? __ldg(&m.bmask[blk8[b]]) : 0ull;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const int hx = b & 1, hy = (b >> 1) & 1, hz = b >> 2;
-      const unsigned long long sten5 = (unsigned long long)(x5[hx] * spread_y(y5[hy])) * spread_z(z5[hz]);
-      const unsigned long long sten3 = (unsigned long long)(x3[hx] * spread_y(y3[hy])) * spread_z(z3[hz]);
-      s_blk[b][tid] = blk8[b];
-      s_cand1[b][tid] = occ[b] & sten3;
-      s_cand2[b][tid] = occ[b] & sten5 & ~sten3;
+      sm.blk[b][tid] = blk8[b];
+      sm.c5[b][tid] = occ[b] & stencil_mask(ax5, ay5, az5, b);
     }
     // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
-    stencil_pass<K, false>(m, s_blk, s_cand1, s_gap, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain);
-    if (!stencil_shell_pass<K>(m, s_blk, s_cand2, s_gap, s_list, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain))
-      stencil_pass<K, false>(m, s_blk, s_cand2, s_gap, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain);  // list overflow: visit all
+    stencil_pass<K, false>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);
+    if (!stencil_shell_pass<K>(m, sm, tid, ix, iy, iz, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain))
+      stencil_pass<K, true>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);  // list overflow: visit the whole shell
     if (a.phase_stats) {  // profiling only: candidate statistics
       atomicAdd(&a.phase_stats[4], n_chain);
       atomicMax(&a.phase_stats[5], n_chain);
@@ -667,24 +818,26 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
   } else {
     done = true;  // unrepresentable / NaN query: no neighbours
   }
-  if (done) {
-    int c = 0;
+  // results so far (final when `done`; otherwise the seed of the exact kernel, which only looks OUTSIDE the stencil)
+  int c = 0;
 #pragma unroll
-    for (int r = 0; r < K; ++r) {
-      const bool ok = t.d[r] < CUDART_INF_F;
-      c += ok ? 1 : 0;
-      float4 o = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_INF_F);
-      if (ok) {
-        const float4 e = (t.id[r] & 0x80000000u) ? __ldg(&m.ovf[t.id[r] & 0x7FFFFFFFu]) : __ldg(&m.slots[t.id[r]]);
-        o = make_float4(e.x, e.y, e.z, t.d[r]);
-      }
-      a.nbr[(size_t)r * a.stride + i] = o;
+  for (int r = 0; r < K; ++r) {
+    const bool ok = t.d[r] < CUDART_INF_F;
+    c += ok ? 1 : 0;
+    float4 o = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_INF_F);
+    if (ok) {
+      const float4 e = (t.id[r] & 0x80000000u) ? __ldg(&m.ovf[t.id[r] & 0x7FFFFFFFu]) : __ldg(&m.slots[t.id[r]]);
+      o = make_float4(e.x, e.y, e.z, t.d[r]);
     }
-    a.cnt[i] = (unsigned char)c;
+    a.nbr[(size_t)r * a.stride + i] = o;
+  }
+  a.cnt[i] = (unsigned char)c;
+  if (done) {
     if (a.phase_stats) atomicAdd(&a.phase_stats[0], 1);
   } else {
     a.worklist[atomicAdd(a.work_count, 1)] = i;
   }
+  FLB_TRACE_END(2 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
 }
 
 __global__ void k_transform(PoseDev s, const float4* __restrict__ body, float4* __restrict__ world, int n) {

@@ -116,6 +116,7 @@ __device__ __forceinline__ void touch_block(const MapDev& m, uint64_t key, int b
 // cls == nullptr: every point; else only points whose class has its bit in cls_mask (bit1: ToAdd, bit2: NoNeed).
 __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
                                int cls_mask, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  FLB_TRACE_BEGIN(7 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -125,12 +126,14 @@ __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const u
     const int bx = voxel_of(p.x, m.ds) >> 2, by = voxel_of(p.y, m.ds) >> 2, bz = voxel_of(p.z, m.ds) >> 2;
     touch_block(m, pack_key(bx, by, bz), bx, by, bz);
   }
+  FLB_TRACE_END(7 * 8);
 }
 
 // ---------------------------------------------------------------------------------------------- K3b: verbatim append
 // Add_Points(..., downsample_on=false) (ikd_Tree.cpp:471-472) and Build (ikd_Tree.cpp:352-364): no dedupe.
 __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
                                 int want_cls, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  FLB_TRACE_BEGIN(10 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -156,6 +159,61 @@ __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const 
     }
     atomicAdd(&m.counters[CNT_VALID], 1);
   }
+  FLB_TRACE_END(10 * 8);
+}
+
+// ---------------------------------------------------------------------------------------------- K3b': chain relocation
+// After a verbatim insert: every voxel that received one of these points and now has >= 2 overflow nodes gets its chain
+// copied into a fresh CONTIGUOUS run of ovf[] (bump allocation; next == this + 1), the old nodes go back to the free
+// stack.  Pure layout optimisation — the chain stays a valid linked list for every reader — so that the k-NN kernels
+// can fetch four nodes per round trip (walk_chain) instead of chasing one pointer per DRAM latency.  One thread per
+// inserted point; the first to set the voxel's bit in the scratch bitmap brel owns the voxel and clears the bit again.
+// Only bump allocation and free-stack pushes happen here (no pops), as the allocator contract requires.
+__global__ void k_relocate_chains(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int want_cls,
+                                  int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  FLB_TRACE_BEGIN(11 * 8);
+  if (skip && *skip) return;
+  if (n_dev) n = *n_dev;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (cls && cls[i] != want_cls) continue;
+    const float4 p = pts[i];
+    if (!coord_ok(p.x, p.y, p.z, m.ds)) continue;
+    const int vx = voxel_of(p.x, m.ds), vy = voxel_of(p.y, m.ds), vz = voxel_of(p.z, m.ds);
+    const int blk = find_block(m, pack_key(vx >> 2, vy >> 2, vz >> 2));
+    if (blk < 0) continue;
+    const int s = (((vz & 3) << 2) + (vy & 3)) * 4 + (vx & 3);
+    const unsigned long long bit = 1ull << s;
+    if (atomicOr((unsigned long long*)&m.brel[blk], bit) & bit) continue;   // another point of this batch owns the voxel
+    const size_t idx = (size_t)blk * 64 + s;
+    // L2-coherent loads (__ldcg): a previous owner of this voxel in this same kernel may have just re-laid the chain
+    const int first = __float_as_int(__ldcg(&m.slots[idx]).w);
+    int L = 0;
+    bool contiguous = true;
+    for (int c = first; c >= 0;) {
+      const int nx = __float_as_int(__ldcg(&m.ovf[c]).w);
+      if (nx >= 0 && nx != c + 1) contiguous = false;
+      ++L;
+      c = nx;
+    }
+    if (L >= 2 && !contiguous) {
+      const int base = atomicAdd(&m.counters[CNT_OVF_BUMP], L);
+      if (base + L <= m.ovf_cap) {
+        int c = first;
+        for (int j = 0; j < L; ++j) {
+          const float4 e = __ldcg(&m.ovf[c]);
+          m.ovf[base + j] = make_float4(e.x, e.y, e.z, __int_as_float(j + 1 < L ? base + j + 1 : -1));
+          free_ovf_node(m, c);
+          c = __float_as_int(e.w);
+        }
+        reinterpret_cast<int*>(&m.slots[idx])[3] = base;
+      } else {
+        atomicSub(&m.counters[CNT_OVF_BUMP], L);   // no room for a run: keep the scattered chain (still correct)
+      }
+    }
+    __threadfence();   // the new layout is visible before the voxel can be owned again
+    atomicAnd((unsigned long long*)&m.brel[blk], ~bit);
+  }
+  FLB_TRACE_END(11 * 8);
 }
 
 // ---------------------------------------------------------------------------------------------- K3c/d: downsampled insert
@@ -187,6 +245,7 @@ __device__ __forceinline__ float dist_pt_to_centre_of(const float4 e, const floa
 __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int n,
                              uint64_t* skeys, unsigned long long* sbest, uint32_t smask, const int* __restrict__ skip,
                              const int* __restrict__ n_dev) {
+  FLB_TRACE_BEGIN(8 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -207,6 +266,7 @@ __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const uns
       s = (s + 1) & smask;
     }
   }
+  FLB_TRACE_END(8 * 8);
 }
 
 // The winning new point of each touched voxel applies the reference's rule against the existing content E of the
@@ -217,6 +277,7 @@ __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const uns
 __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int n,
                            const uint64_t* __restrict__ skeys, const unsigned long long* __restrict__ sbest,
                            uint32_t smask, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  FLB_TRACE_BEGIN(9 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -279,6 +340,7 @@ __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsig
       atomicAdd(&m.counters[CNT_SCRATCH0], 1);
     }
   }
+  FLB_TRACE_END(9 * 8);
 }
 
 // ---------------------------------------------------------------------------------------------- block iteration helpers

@@ -162,7 +162,7 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&P)[5][3], float thr
 }
 
 // ---------------------------------------------------------------------------------------------- K1': residual + H^T H
-constexpr int MEAS_THREADS = 256;
+constexpr int MEAS_THREADS = 512;   // one CTA per SM: half as many per-block partials for the update kernel to reduce
 constexpr int NACC = 93;  // 91 upper-triangular entries of [h_x | h]^T [h_x | h] (13x13) + total_residual + M
 
 struct MeasArgs {
@@ -244,18 +244,24 @@ __device__ __forceinline__ bool select_point(const MeasArgs& a, int i, int searc
 }
 
 template <bool EXTR>
+constexpr int meas_smem_bytes() { return (MEAS_THREADS / 32) * 32 * (EXTR ? 13 : 7) * (int)sizeof(double); }
+
+template <bool EXTR>
 __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
   constexpr int W = EXTR ? 13 : 7;               // augmented row width [cols..., h]
   constexpr int NE = W * (W + 1) / 2;            // 91 or 28
   constexpr int EPL = (NE + 31) / 32;            // entries per lane
-  __shared__ double tile[MEAS_THREADS / 32][32][W + 0];
-  __shared__ double wacc[MEAS_THREADS / 32][NACC];
+  // dynamic shared memory (meas_smem_bytes): the per-warp row tiles; reused for the per-warp totals after the loop
+  extern __shared__ double meas_smem[];
+  double (*tile)[32][W] = reinterpret_cast<double (*)[32][W]>(meas_smem);
+  double (*wacc)[96] = reinterpret_cast<double (*)[96]>(meas_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.0;
   double rsum = 0.0;
   int msum = 0;
+  FLB_TRACE_BEGIN(4 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !ctl_pass_active(a.ctl)) return;   // the iterated update already finished (block-uniform)
   const PoseDev pose = a.ctl ? a.ctl->pose : a.pose;
   const int search = a.ctl ? a.ctl->converge : a.search;
@@ -313,6 +319,7 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
     rsum += __shfl_xor_sync(FULL, rsum, o);
     msum += __shfl_xor_sync(FULL, msum, o);
   }
+  __syncthreads();   // every warp is done with its tile: the region now holds the per-warp totals
   for (int e = lane; e < NACC; e += 32) wacc[warp][e] = 0.0;
   __syncwarp();
 #pragma unroll
@@ -339,6 +346,7 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
     for (int w = 0; w < MEAS_THREADS / 32; ++w) s += wacc[w][e];
     a.partial[(size_t)blockIdx.x * NACC + e] = s;
   }
+  FLB_TRACE_END(4 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
 }
 
 // K2: fixed-order final reduction of the per-block partials -> out[NACC]
@@ -377,6 +385,7 @@ __global__ void k_sel_to_int(const unsigned char* __restrict__ sel, int* __restr
 __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __restrict__ body, const float4* __restrict__ nbr,
                            const unsigned char* __restrict__ cnt, int n_in, int nbr_stride, int flg_in, double fs,
                            float4* __restrict__ world, unsigned char* __restrict__ cls, int* counts) {
+  FLB_TRACE_BEGIN(6 * 8);
   if (ctl && ctl->need_host) return;  // the host fallback redoes update + insert for this scan
   const PoseDev s = ctl ? ctl->pose : s_in;
   const int n = ctl ? ctl->n : n_in;
@@ -422,6 +431,7 @@ __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __re
       if (b2) atomicAdd(&counts[1], __popc(b2));
     }
   }
+  FLB_TRACE_END(6 * 8);
 }
 
 }  // namespace flb

@@ -12,12 +12,16 @@
 //   slots[B*64]       float4 head point of each voxel: x,y,z and w = int index of an overflow node (-1: none).
 //                     INVARIANT: w == -1 whenever the voxel has no overflow chain (also while the voxel is empty).
 //   ovf[O]            float4 overflow nodes (x,y,z, w = next) for the rare voxels holding > 1 point
-//                     (first Build, no-downsample inserts: SURVEY.md §3.3)
+//                     (first Build, no-downsample inserts: SURVEY.md §3.3).  A linked list per voxel; after every
+//                     verbatim insert the chains it touched are re-laid CONTIGUOUSLY (k_relocate_chains: next == this + 1),
+//                     so readers fetch four consecutive nodes per round trip and only fall back to pointer chasing
+//                     when a link does not confirm the guess (walk_chain).
 //   bkey[B]           key of each allocated block (EMPTY if free) — lets delete/flatten iterate blocks densely
 //   ckeys[CC]/cbits[CC*8]  coarse hash + bitmaps
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "trace.cuh"
 
 namespace flb {
 
@@ -58,6 +62,7 @@ struct MapDev {
   float4* slots;
   float4* ovf;
   uint64_t* bkey;
+  uint64_t* brel;        // per-block scratch bitmap of k_relocate_chains (all zero between kernels)
   uint32_t* free_blk;
   uint32_t* free_ovf;
   uint64_t* ckeys;
@@ -92,6 +97,33 @@ __host__ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
 
 // voxel index of a coordinate: the reference's floor(x/downsample_size) in float (ikd_Tree.cpp:424).
 __device__ __forceinline__ int voxel_of(float x, float ds) { return (int)floorf(__fdiv_rn(x, ds)); }
+
+// Visit every node of the overflow chain starting at node c: f(node, index).  Speculates that the chain is laid out
+// contiguously (see MapDev::ovf): nodes c..c+3 are loaded together (64 B, at most two sectors) and consumed while the
+// links confirm next == this + 1; otherwise the real link is followed.  Reading past a chain's end stays inside ovf[].
+template <class F>
+__device__ __forceinline__ void walk_chain(const MapDev& m, int c, F&& f) {
+  while (c >= 0) {
+    if (c + 3 < m.ovf_cap) {
+      const float4 o0 = __ldg(&m.ovf[c]), o1 = __ldg(&m.ovf[c + 1]), o2 = __ldg(&m.ovf[c + 2]), o3 = __ldg(&m.ovf[c + 3]);
+      f(o0, c);
+      int nx = __float_as_int(o0.w);
+      if (nx != c + 1) { c = nx; continue; }
+      f(o1, c + 1);
+      nx = __float_as_int(o1.w);
+      if (nx != c + 2) { c = nx; continue; }
+      f(o2, c + 2);
+      nx = __float_as_int(o2.w);
+      if (nx != c + 3) { c = nx; continue; }
+      f(o3, c + 3);
+      c = __float_as_int(o3.w);
+    } else {
+      const float4 o = __ldg(&m.ovf[c]);
+      f(o, c);
+      c = __float_as_int(o.w);
+    }
+  }
+}
 
 // Block lookup (read-only). Returns block index or -1.
 __device__ __forceinline__ int find_block(const MapDev& m, uint64_t key) {
