@@ -29,11 +29,16 @@ constexpr int BLOCK_RINGS = 3;  // block shells searched by the exact kernel bef
 constexpr int KNN_THREADS = FLB_KNN_THREADS;
 constexpr int KNN_MIN_CTAS = FLB_KNN_MINB;
 
+// Large K (generic Nearest_Search with k up to 20, off the hot path) keeps its list loops ROLLED: the lists then live
+// in local memory, but the fully unrolled lexicographic insert at every inlined call site made that instantiation
+// 90 % of the translation unit (minutes of ptxas time) for a path that is never timed.
+__host__ __device__ constexpr int topk_unroll(int k) { return k <= 8 ? k : 1; }
+
 template <int K>
 struct TopK {
   float d[K], x[K], y[K], z[K];
   __device__ __forceinline__ void clear() {
-#pragma unroll
+#pragma unroll (topk_unroll(K))
     for (int j = 0; j < K; ++j) { d[j] = CUDART_INF_F; x[j] = 0.f; y[j] = 0.f; z[j] = 0.f; }
   }
   static __device__ __forceinline__ bool less(float da, float xa, float ya, float za, float db, float xb, float yb, float zb) {
@@ -45,7 +50,7 @@ struct TopK {
   __device__ __forceinline__ void insert(float dd, float px, float py, float pz) {
     if (!less(dd, px, py, pz, d[K - 1], x[K - 1], y[K - 1], z[K - 1])) return;
     d[K - 1] = dd; x[K - 1] = px; y[K - 1] = py; z[K - 1] = pz;
-#pragma unroll
+#pragma unroll (topk_unroll(K))
     for (int j = K - 1; j > 0; --j) {
       if (less(d[j], x[j], y[j], z[j], d[j - 1], x[j - 1], y[j - 1], z[j - 1])) {
         float t;
@@ -57,7 +62,7 @@ struct TopK {
     }
   }
   __device__ __forceinline__ void pop_front() {
-#pragma unroll
+#pragma unroll (topk_unroll(K))
     for (int j = 0; j < K - 1; ++j) { d[j] = d[j + 1]; x[j] = x[j + 1]; y[j] = y[j + 1]; z[j] = z[j + 1]; }
     d[K - 1] = CUDART_INF_F;
   }
