@@ -76,6 +76,9 @@ EXPORTS = [
     "flb_scan_set_device", "flb_pass", "flb_pass_rows", "flb_esikf_update", "flb_map_incremental",
     "flb_neighbors_download", "flb_fov_segment", "flb_scan_step", "flb_session_stream", "flb_session_sync",
     "flb_map_profile_enable", "flb_map_profile_read", "flb_session_set_update_engine", "flb_scan_prefetch", "flb_scan_step_begin", "flb_scan_step_finish",
+    "flb_frontend_create", "flb_frontend_destroy", "flb_frontend_upload", "flb_frontend_undistort",
+    "flb_frontend_voxel_filter", "flb_frontend_download_undistorted", "flb_frontend_download_down",
+    "flb_frontend_points_to_world", "flb_voxel_grid_filter", "flb_map_reconstruct_keyframes",
 ]
 
 
@@ -131,6 +134,18 @@ def lib():
         L.flb_session_set_update_engine.argtypes = [vp, C.c_int]
         L.flb_map_profile_enable.argtypes = [vp, C.c_int]
         L.flb_map_profile_read.argtypes = [vp, C.POINTER(Profile), C.c_int]
+        L.flb_frontend_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.flb_frontend_destroy.argtypes = [vp]
+        L.flb_frontend_destroy.restype = None
+        L.flb_frontend_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.flb_frontend_undistort.argtypes = [vp, dp, C.c_int, dp]
+        L.flb_frontend_voxel_filter.argtypes = [vp, C.c_float, ip]
+        L.flb_frontend_download_undistorted.argtypes = [vp, fp, fp, vp, C.c_int, ip]
+        L.flb_frontend_download_down.argtypes = [vp, fp, fp, C.c_int, ip]
+        L.flb_frontend_points_to_world.argtypes = [vp, C.c_int, dp, fp, C.c_int, ip]
+        L.flb_voxel_grid_filter.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, fp, C.c_int, ip]
+        L.flb_map_reconstruct_keyframes.argtypes = [vp, C.POINTER(vp), ip, C.c_int, C.c_int, C.c_int, fp, C.c_float, fp,
+                                                    C.c_int, ip]
         _lib = L
     return _lib
 
@@ -401,6 +416,115 @@ class Session:
 
     def sync(self):
         _chk(lib().flb_session_sync(self.h))
+
+
+POINT_STRIDE = 48      # pcl::PointXYZINormal (PointType, common_lib.h:161)
+OFF_INTENSITY = 32
+OFF_CURVATURE = 36
+
+
+def pack_pointtype(xyz, intensity=None, curvature=None):
+    """Host buffer of n reference PointType records (48 B: x,y,z,_, nx,ny,nz,_, intensity,curvature,_,_)."""
+    xyz = np.asarray(xyz, np.float32)
+    buf = np.zeros((len(xyz), 12), np.float32)
+    buf[:, 0:3] = xyz[:, :3]
+    if intensity is not None:
+        buf[:, 8] = intensity
+    if curvature is not None:
+        buf[:, 9] = curvature
+    return buf
+
+
+class FrontEnd:
+    """Device front end of one session: meas.lidar -> UndistortPcl -> VoxelGrid -> feats_down_body."""
+
+    def __init__(self, session, max_raw_points=262144):
+        self.session = session
+        self.cap = int(max_raw_points)
+        self.h = C.c_void_p()
+        _chk(lib().flb_frontend_create(session.h, self.cap, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().flb_frontend_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, points48):
+        """points48: (n,12) float32 PointType records (see pack_pointtype)."""
+        b = np.ascontiguousarray(points48, np.float32)
+        assert b.ndim == 2 and b.shape[1] == 12
+        _chk(lib().flb_frontend_upload(self.h, _p(b), len(b), POINT_STRIDE, OFF_INTENSITY, OFF_CURVATURE))
+        self.n_raw = len(b)
+
+    def upload_ptr(self, ptr, n, stride=POINT_STRIDE, off_i=OFF_INTENSITY, off_c=OFF_CURVATURE):
+        _chk(lib().flb_frontend_upload(self.h, C.c_void_p(ptr), int(n), stride, off_i, off_c))
+        self.n_raw = int(n)
+
+    def undistort(self, imu_poses, state26_end):
+        poses = np.ascontiguousarray(imu_poses, np.float64).reshape(-1, 22)
+        st = np.ascontiguousarray(state26_end, np.float64)
+        _chk(lib().flb_frontend_undistort(self.h, _p(poses), len(poses), _p(st)))
+
+    def voxel_filter(self, leaf):
+        n = C.c_int(0)
+        _chk(lib().flb_frontend_voxel_filter(self.h, float(leaf), C.byref(n)))
+        self.session.n = n.value
+        return n.value
+
+    def download_undistorted(self):
+        n = self.n_raw
+        xyzi = np.empty((max(n, 1), 4), np.float32)
+        cur = np.empty(max(n, 1), np.float32)
+        perm = np.empty(max(n, 1), np.int32)
+        cnt = C.c_int(0)
+        _chk(lib().flb_frontend_download_undistorted(self.h, _p(xyzi), _p(cur), _p(perm), n, C.byref(cnt)))
+        return xyzi[:n], cur[:n], perm[:n]
+
+    def download_down(self):
+        cnt = C.c_int(0)
+        _chk(lib().flb_frontend_download_down(self.h, None, None, 0, C.byref(cnt)))
+        n = cnt.value
+        xyzi = np.empty((max(n, 1), 4), np.float32)
+        cur = np.empty(max(n, 1), np.float32)
+        _chk(lib().flb_frontend_download_down(self.h, _p(xyzi), _p(cur), n, C.byref(cnt)))
+        return xyzi[:n], cur[:n]
+
+    def points_to_world(self, which, state26):
+        st = np.ascontiguousarray(state26, np.float64)
+        cnt = C.c_int(0)
+        out = np.empty((self.cap, 4), np.float32)
+        _chk(lib().flb_frontend_points_to_world(self.h, int(which), _p(st), _p(out), self.cap, C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+
+def voxel_grid_filter(tree, points48, leaf):
+    """pcl::VoxelGrid centroid filter of a host cloud of PointType records -> (m,4) x,y,z,intensity."""
+    b = np.ascontiguousarray(points48, np.float32)
+    out = np.empty((max(len(b), 1), 4), np.float32)
+    n = C.c_int(0)
+    _chk(lib().flb_voxel_grid_filter(tree.h, _p(b), len(b), POINT_STRIDE, OFF_INTENSITY, float(leaf), _p(out), len(out), C.byref(n)))
+    return out[:n.value].copy()
+
+
+def reconstruct_keyframes(tree, clouds48, poses6, leaf):
+    """recontructIKdTree's data-parallel part: transform + concatenate + VoxelGrid + reconstruct. Returns featsFromMap."""
+    clouds = [np.ascontiguousarray(c, np.float32) for c in clouds48]
+    k = len(clouds)
+    ptrs = (C.c_void_p * max(k, 1))(*[c.ctypes.data for c in clouds])
+    sizes = (C.c_int * max(k, 1))(*[len(c) for c in clouds])
+    p6 = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
+    total = sum(len(c) for c in clouds)
+    out = np.empty((max(total, 1), 4), np.float32)
+    n = C.c_int(0)
+    _chk(lib().flb_map_reconstruct_keyframes(tree.h, ptrs, sizes, k, POINT_STRIDE, OFF_INTENSITY, _p(p6), float(leaf), _p(out),
+                                             len(out), C.byref(n)))
+    return out[:n.value].copy()
 
 
 def make_fov(cube_len=200.0, det_range=100.0):

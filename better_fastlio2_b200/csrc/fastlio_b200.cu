@@ -1398,3 +1398,6 @@ extern "C" int flb_debug_trace_read(unsigned long long* out, long long* phases, 
   return 0;
 }
 #endif
+
+// ------------------------------------------------------------------------------------------------ front-end rows
+#include "frontend_host.cuh"

@@ -254,3 +254,48 @@ def trajectory_state(k, speed=10.0, dt=0.1, z=1.8, yaw_amp_deg=4.0, start=(0.0, 
     q = quat_from_rotvec([0.0, 0.0, yaw])
     y = start[1] + 1.5 * np.sin(0.02 * k)
     return make_state(pos=(x, y, z), rot=q, vel=(speed, 0, 0))
+
+
+# ------------------------------------------------------------------------------------------------ front-end inputs
+def imu_pose_sequence(state0, rng, n_imu=21, scan_time=0.1, first_offset=0.002):
+    """A plausible IMUpose vector (IMU_Processing.hpp:260-322) for one scan: n_imu+1 Pose6D records of 22 doubles
+    (offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9] row-major); record 0 is the previous posterior at offset 0.
+    Returns (poses[n_imu+1,22], state26_end) where state26_end is the propagated state at the last record."""
+    st = np.array(state0, np.float64).copy()
+    R = quat_to_mat(st[3:7])
+    vel = np.array([10.0, 0.3, 0.0]) + rng.normal(0, 0.1, 3)
+    pos = st[0:3].copy()
+    gyr = np.array([0.02, -0.03, 0.25]) + rng.normal(0, 0.02, 3)
+    acc = np.array([0.4, -0.2, 0.1]) + rng.normal(0, 0.05, 3)
+    poses = [np.concatenate([[0.0], acc, gyr, vel, pos, R.reshape(-1)])]
+    t_prev = 0.0
+    for k in range(n_imu):
+        t = first_offset + k * (scan_time / max(n_imu - 1, 1))
+        dt = t - t_prev
+        g = gyr + rng.normal(0, 0.01, 3)
+        a = acc + rng.normal(0, 0.05, 3)
+        R = R @ quat_to_mat(quat_from_rotvec(g * dt))
+        pos = pos + vel * dt + 0.5 * a * dt * dt
+        vel = vel + a * dt
+        poses.append(np.concatenate([[t], a, g, vel, pos, R.reshape(-1)]))
+        t_prev = t
+    end = st.copy()
+    end[0:3] = pos
+    end[14:17] = vel
+    # rotation matrix -> quaternion (x,y,z,w)
+    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
+    end[3:7] = [(R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w), w]
+    return np.array(poses, np.float64), end
+
+
+def raw_scan_with_times(body_xyz, rng, scan_time_ms=100.0, shuffle=True):
+    """Attach intensity and per-point time offsets (curvature, ms — preprocess.cpp) to a scan; the returns arrive in
+    azimuth order with a few exact zeros and exact duplicates, as real drivers produce."""
+    n = len(body_xyz)
+    az = np.arctan2(body_xyz[:, 1], body_xyz[:, 0])
+    cur = ((az + np.pi) / (2 * np.pi) * scan_time_ms).astype(np.float32)
+    cur[rng.integers(0, n, max(1, n // 500))] = 0.0
+    cur = np.round(cur * 8.0) / 8.0   # quantised stamps -> many exact ties
+    inten = rng.uniform(0, 255, n).astype(np.float32)
+    order = rng.permutation(n) if shuffle else np.arange(n)
+    return body_xyz[order].astype(np.float32), inten[order], cur[order].astype(np.float32)

@@ -216,6 +216,55 @@ int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const float* body_xy
                         const double* state26, const double* P, int flg_EKF_inited);
 int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* state26, double* P, flb_scan_result* out);
 
+/* ------------------------------------------------------------------------------------------------ front-end rows
+ * The callers / data formats either side of the per-scan path, so that a raw scan never leaves the
+ * GPU between the driver callback and the update:
+ *   meas.lidar --UndistortPcl--> feats_undistort --downSizeFilterSurf.filter--> feats_down_body --> flb_scan_step
+ * A front end belongs to one session and shares its stream; calls are serialised by the caller like all others.
+ * Points are the reference's PointType (pcl::PointXYZINormal, common_lib.h:161): 48-byte stride, x@0 y@4 z@8,
+ * intensity@32, curvature@36 (= time offset in ms, preprocess.cpp) — stride and offsets are parameters. */
+typedef struct flb_frontend flb_frontend;
+#define FLB_IMU_POSE_DOUBLES 22 /* Pose6D (msg/Pose6D.msg, set_pose6d common_lib.h:446-460):
+                                   offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9] row-major */
+#define FLB_MAX_IMU_POSES 256
+
+int flb_frontend_create(flb_session* s, int max_raw_points, flb_frontend** out);
+void flb_frontend_destroy(flb_frontend* f);
+/* meas.lidar (IMU_Processing.hpp:242 "pcl_out = *(meas.lidar)"): upload the raw scan. off_intensity / off_curvature are
+ * byte offsets of those float fields inside a point, or -1 when absent (treated as 0). */
+int flb_frontend_upload(flb_frontend* f, const void* pts, int n, int stride_bytes, int off_intensity, int off_curvature);
+/* ImuProcess::UndistortPcl, the per-point part (IMU_Processing.hpp:243 sort by time, :334-386 backward compensation).
+ * imu_poses = n_poses x 22 doubles = the IMUpose vector built by the forward propagation (:260-322, stays on the host
+ * with kf.predict); state26_end = imu_state after the last predict (:329).  Result: feats_undistort in time order
+ * (ties keep upload order; the reference's std::sort leaves them unspecified). */
+int flb_frontend_undistort(flb_frontend* f, const double* imu_poses, int n_poses, const double* state26_end);
+/* downSizeFilterSurf.setInputCloud(feats_undistort); downSizeFilterSurf.filter(*feats_down_body)
+ * (laserMapping.cpp:2322-2323, leaf = mappingSurfLeafSize :2135): pcl::VoxelGrid centroid filter (PCL 1.10 semantics:
+ * float leaf index relative to the cloud minimum, output ordered by leaf index, centroid of x,y,z,intensity,curvature;
+ * PCL's int32 overflow guard returns the input unchanged).  The result becomes the session's current scan
+ * (as flb_scan_upload would); *n_out = feats_down_size.  Sums run in time order inside a leaf (PCL: unspecified). */
+int flb_frontend_voxel_filter(flb_frontend* f, float leaf_size, int* n_out);
+/* Read back feats_undistort (x,y,z,intensity per point; curvature; perm[j] = upload index of sorted point j) and
+ * feats_down_body.  Any output pointer may be NULL; at most cap points are written, *n = the cloud size. */
+int flb_frontend_download_undistorted(flb_frontend* f, float* out_xyzi, float* out_curvature, int* out_perm, int cap, int* n);
+int flb_frontend_download_down(flb_frontend* f, float* out_xyzi, float* out_curvature, int cap, int* n);
+/* publish_frame_world / map saving (laserMapping.cpp:1502-1540): RGBpointBodyToWorld (:1101-1110) of every point of
+ * feats_down_body (which = 0, dense_pub_en false) or feats_undistort (which = 1) with the posterior state. */
+int flb_frontend_points_to_world(flb_frontend* f, int which, const double* state26, float* out_xyzi, int cap, int* n);
+
+/* Stand-alone pcl::VoxelGrid centroid filter on a host cloud (the reference's other VoxelGrid call sites, e.g.
+ * laserMapping.cpp:640-643, :1780-1789), run on the map's device/stream.  out_xyzi = x,y,z,intensity per point. */
+int flb_voxel_grid_filter(flb_map* m, const void* pts, int n, int stride_bytes, int off_intensity, float leaf_size,
+                          float* out_xyzi, int cap, int* n_out);
+/* recontructIKdTree, the data-parallel part (laserMapping.cpp:632-664): for the selected key frames k (clouds[k] with
+ * sizes[k] points in the key frame's own frame, poses6[k] = x,y,z,roll,pitch,yaw of cloudKeyPoses6D) do
+ * subMap += transformPointCloud(cloud_k, pose_k) (common_lib.h:711-734), VoxelGrid(leaf), ikdtree.reconstruct(result).
+ * The filtered sub-map (featsFromMap, :664) is returned in out_xyzi (up to cap points); *n_points = its size.  The
+ * key-frame selection itself (pose radius search, :621-635) is back-end bookkeeping and stays with the caller. */
+int flb_map_reconstruct_keyframes(flb_map* m, const void* const* clouds, const int* sizes, int n_keyframes, int stride_bytes,
+                                  int off_intensity, const float* poses6, float leaf_size, float* out_xyzi, int cap,
+                                  int* n_points);
+
 /* Stream access for callers that overlap work (returns a cudaStream_t as void*). */
 void* flb_session_stream(flb_session* s);
 int flb_session_sync(flb_session* s);

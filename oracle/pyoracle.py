@@ -61,6 +61,13 @@ def lio():
         L.orc_invert.argtypes = [f64p, f64p, C.c_int]
         L.orc_invert.restype = C.c_int
         L.orc_s2_mats.argtypes = [f64p, f64p, f64p, f64p, f64p]
+        # front-end rows (frontend_oracle.cpp)
+        L.orc_undistort.argtypes = [f32p, f32p, C.c_int, f64p, C.c_int, f64p, f32p, i32p]
+        L.orc_voxel_grid.argtypes = [f32p, C.c_void_p, C.c_int, C.c_float, C.c_int, f32p, C.c_void_p]
+        L.orc_voxel_grid.restype = C.c_int
+        L.orc_rpy_matrix.argtypes = [f32p, f32p]
+        L.orc_transform_cloud_rpy.argtypes = [f32p, C.c_int, f32p, f32p]
+        L.orc_body_to_world4.argtypes = [f64p, f32p, C.c_int, f32p]
         for pre in ("mapport",):
             _bind_map(L, pre)
         L.mapport_create.argtypes = [C.c_float]
@@ -320,3 +327,50 @@ def esti_plane(nn5x3, thr=0.1):
     out = np.zeros(4, np.float32)
     ok = lio().orc_esti_plane(np.ascontiguousarray(nn5x3, np.float32).reshape(-1), thr, out)
     return bool(ok), out
+
+
+# ------------------------------------------------------------------------------------------------ front-end rows
+def undistort(xyz, curvature, poses, state26):
+    """UndistortPcl backward pass (IMU_Processing.hpp:241-243,334-386). Returns (xyz_sorted[n,3], perm[n])."""
+    xyz = _xyz(xyz)
+    cur = np.ascontiguousarray(curvature, dtype=np.float32)
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 22)
+    out = np.empty_like(xyz)
+    perm = np.empty(len(xyz), dtype=np.int32)
+    lio().orc_undistort(xyz, cur, len(xyz), poses, len(poses), np.ascontiguousarray(state26, dtype=np.float64), out, perm)
+    return out, perm
+
+
+def voxel_grid(pts4, leaf, curvature=None, order="pcl"):
+    """pcl::VoxelGrid centroid filter (PCL 1.10 restated). pts4 = [n,4] x,y,z,intensity. order 'pcl' | 'stable'.
+    Returns (out4[m,4], out_curv[m] or None, overflow flag)."""
+    pts4 = np.ascontiguousarray(pts4, dtype=np.float32)
+    n = len(pts4)
+    out = np.empty((max(n, 1), 4), dtype=np.float32)
+    cur = None if curvature is None else np.ascontiguousarray(curvature, dtype=np.float32)
+    oc = None if cur is None else np.empty(max(n, 1), dtype=np.float32)
+    m = lio().orc_voxel_grid(pts4, None if cur is None else cur.ctypes.data, n, float(leaf), 0 if order == "pcl" else 1, out,
+                             None if oc is None else oc.ctypes.data)
+    ovf = m < 0
+    m = n if ovf else m
+    return out[:m].copy(), (None if oc is None else oc[:m].copy()), ovf
+
+
+def rpy_matrix(pose6):
+    t = np.empty(12, dtype=np.float32)
+    lio().orc_rpy_matrix(np.ascontiguousarray(pose6, dtype=np.float32), t)
+    return t.reshape(3, 4)
+
+
+def transform_cloud_rpy(pts4, pose6):
+    pts4 = np.ascontiguousarray(pts4, dtype=np.float32)
+    out = np.empty_like(pts4)
+    lio().orc_transform_cloud_rpy(pts4, len(pts4), np.ascontiguousarray(pose6, dtype=np.float32), out)
+    return out
+
+
+def body_to_world4(state26, pts4):
+    pts4 = np.ascontiguousarray(pts4, dtype=np.float32)
+    out = np.empty_like(pts4)
+    lio().orc_body_to_world4(np.ascontiguousarray(state26, dtype=np.float64), pts4, len(pts4), out)
+    return out
