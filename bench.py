@@ -299,6 +299,7 @@ def run_b200(args):
         npts_prof += len(work["scans"][k])
     prof = tree.profile_read(reset=True)
     tree.profile_enable(False)
+    frontend = frontend_rows(work, ses, fov, torch, local, W, rank) if not TINY else None
     ms_max, e2e_ms_max = dist_max([ms, e2e_s * 1e3], device=f"cuda:{local}")
     stats = tree.stats()
     if rank == 0:
@@ -349,6 +350,8 @@ def run_b200(args):
             "map_stats": {k: stats[k] for k in ("blocks_in_use", "overflow_in_use", "coarse_cells", "hash_tombstones")},
             "clocks": clk,
         }
+        if frontend:
+            out["frontend"] = frontend
         if world_size == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(work, W)
         print(json.dumps(out), flush=True)
@@ -356,6 +359,71 @@ def run_b200(args):
     tree.close()
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def frontend_rows(work, ses, fov, torch, local, W, rank, S=20, leaf=0.5):
+    """SURVEY.md §8f rows measured beside the headline (NOT part of `value`/`e2e`): the raw 120k-point scan goes
+    host -> UndistortPcl backward pass -> pcl::VoxelGrid(leaf) -> update -> map_incremental ("Q-ds" query mode: the queries
+    are the filtered scan, as laserMapping.cpp:2322 does), all through the C ABI from pinned host buffers; the CPU figure
+    is the oracle's restatement of the same two front-end steps on one core (PCL / the reference run them serially)."""
+    from better_fastlio2_b200 import capi, synth
+    rng = np.random.default_rng(99 + rank)
+    nmax = max(len(s) for s in work["scans"])
+    fe = capi.FrontEnd(ses, max_raw_points=max(131072, nmax))
+    ks = list(range(W, W + S))
+    raw, poses, ends = [], [], []
+    for k in ks:
+        xyz, inten, cur = synth.raw_scan_with_times(work["scans"][k], rng, shuffle=False)
+        raw.append(torch.from_numpy(capi.pack_pointtype(xyz, inten, cur)).pin_memory())
+        # a sensor (almost) at rest during the sweep: the synthetic scans carry no motion distortion, so the compensation
+        # must stay ~identity while still running its full arithmetic (non-zero gyro -> Rodrigues path)
+        st = work["priors"][k]
+        R = synth.quat_to_mat(st[3:7]).reshape(-1)
+        pz = [np.concatenate([[0.005 * j], [1e-4, 0, 0], [1e-5, 2e-5, -1e-5], [1e-4, 0, 0], st[0:3], R]) for j in range(21)]
+        pz[0][0] = 0.0
+        poses.append(np.array(pz))
+        ends.append(st.copy())
+    P0 = work["P"]
+
+    def one(i, with_step=True):
+        fe.upload_ptr(raw[i].data_ptr(), raw[i].shape[0])
+        fe.undistort(poses[i], ends[i])
+        n = fe.voxel_filter(leaf)
+        if with_step:
+            st, P = work["priors"][ks[i]].copy(), P0.copy()
+            ses.scan_step_ptr(fov, None, 0, 0, st, P)
+        return n
+
+    one(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nd = [one(i, with_step=False) for i in range(S)]
+    torch.cuda.synchronize()
+    t_front = (time.perf_counter() - t0) / S
+    t0 = time.perf_counter()
+    for i in range(S):
+        one(i)
+    torch.cuda.synchronize()
+    t_all = (time.perf_counter() - t0) / S
+    out = {"what": "raw scan (host, 48-B PointType) -> undistort -> VoxelGrid -> update -> map_incremental; wall clock, host buffers",
+           "leaf": leaf, "raw_points_mean": float(np.mean([r.shape[0] for r in raw])), "down_points_mean": float(np.mean(nd)),
+           "front_ms_per_scan": 1e3 * t_front, "scans_per_s_raw_to_posterior": 1.0 / t_all, "samples": S,
+           "h2d_bytes_per_scan": int(48 * np.mean([r.shape[0] for r in raw]))}
+    if rank == 0:
+        try:
+            from oracle import pyoracle as po
+            t0 = time.perf_counter()
+            for i in range(3):
+                a = raw[i].numpy()
+                ox, op = po.undistort(a[:, 0:3].copy(), a[:, 9].copy(), poses[i], ends[i])
+                po.voxel_grid(np.column_stack([ox, a[op, 8]]), leaf, order="pcl")
+            out["cpu_front_ms_per_scan"] = 1e3 * (time.perf_counter() - t0) / 3
+            out["cpu_kind"] = "port (oracle restatement of UndistortPcl backward pass + PCL 1.10 VoxelGrid), 1 core"
+        except Exception as e:   # the oracle is test infrastructure: its absence must not break the bench line
+            out["cpu_front_ms_per_scan"] = None
+            out["cpu_kind"] = f"unavailable: {e}"
+    fe.close()
+    return out
 
 
 def cpu_baseline(work, W):

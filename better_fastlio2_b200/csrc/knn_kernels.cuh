@@ -441,9 +441,9 @@ __device__ __noinline__ void warp_finish_coarse(MapDev m, float4* nbr, unsigned 
 //     kernel is a chain of dependent DRAM/L2 round trips per query, i.e. bound by queries in flight x latency);
 //   * the rare query still unresolved after ring 3 (2.4 m at 0.2 m voxels; map frontier) is finished by the WHOLE warp
 //     over the coarse levels: 3x3x3 coarse cells, then every remaining coarse cell with box-distance pruning.
-template <int K>
+template <int K, int G>   // G = lanes per query (group lane r must be able to hold result r: G >= K)
 __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
-  constexpr int G = (K <= 8) ? 8 : 32;   // lanes per query (group lane r must be able to hold result r: G >= K)
+  static_assert(G >= K && (G == 8 || G == 32), "group width");
   constexpr int QPW = 32 / G;            // queries per warp
   const MapDev& m = a.m;
   const int lane = threadIdx.x & 31;

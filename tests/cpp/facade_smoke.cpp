@@ -9,6 +9,7 @@
 
 #include <fastlio_b200/ikd_tree_facade.hpp>
 #include <fastlio_b200/lio_gpu_frontend.hpp>
+#include <fastlio_b200/scan_frontend_facade.hpp>
 
 typedef pcl::PointXYZINormal PointType;                       // common_lib.h:161
 typedef std::vector<PointType, Eigen::aligned_allocator<PointType>> PointVector;  // common_lib.h:163
@@ -20,6 +21,9 @@ struct state_ikfom { Vec3 pos; Quat rot; Quat offset_R_L_I; Vec3 offset_T_L_I, v
 struct MatX { std::vector<double> a; int r = 0, c = 0; void resize(int R, int C) { r = R; c = C; a.assign((size_t)R * C, 0.0); } double* data() { return a.data(); } int rows() const { return r; } };
 struct VecX { std::vector<double> a; void resize(int n) { a.assign(n, 0.0); } double* data() { return a.data(); } };
 struct dyn_share_datastruct { bool valid = true, converge = true; MatX h_x; VecX h; };
+
+struct Pose6D { double offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]; };   // msg/Pose6D.msg
+struct PointCloudXYZI { PointVector points; };                                    // pcl::PointCloud<PointType> look-alike
 
 KD_TREE<PointType> ikdtree;  // laserMapping.cpp:116
 flb::LioGpu gpu;
@@ -85,6 +89,49 @@ int main() {
     }
   if (maxerr > 1e-9 * scale) { std::printf("HTH mismatch %g / %g\n", maxerr, scale); return 11; }
   const int added = gpu.map_incremental(s, true);
+
+  // ---- front-end facades: UndistortPcl backward pass -> VoxelGrid -> h_share_model without a host round trip
+  flb::ScanFrontEnd fe;
+  if (!fe.attach(gpu.handle(), 1 << 17)) return 12;
+  PointCloudXYZI lidar, pcl_out, feats_down_body, world;
+  for (size_t i = 0; i < body.size(); ++i) {
+    PointType p = body[i];
+    p.intensity = (float)(i % 200);
+    p.curvature = (float)((i * 37) % 1000) * 0.1f;   // 0..99.9 ms, shuffled
+    lidar.points.push_back(p);
+  }
+  std::vector<Pose6D> IMUpose(3);
+  for (int k = 0; k < 3; ++k) {   // a sensor at rest: the compensation must be the identity
+    Pose6D q{};
+    q.offset_time = 0.05 * k;
+    for (int i = 0; i < 3; ++i) q.pos[i] = s.pos.v[i];
+    q.rot[0] = q.rot[4] = q.rot[8] = 1.0;
+    IMUpose[k] = q;
+  }
+  if (!fe.undistort(lidar, IMUpose, s, &pcl_out) || pcl_out.points.size() != lidar.points.size()) return 13;
+  double sum_in = 0, sum_out = 0;
+  for (size_t i = 0; i < lidar.points.size(); ++i) {
+    if (i && pcl_out.points[i].curvature < pcl_out.points[i - 1].curvature) return 14;   // time order
+    sum_in += (double)lidar.points[i].x + lidar.points[i].y + lidar.points[i].z + lidar.points[i].intensity;
+    sum_out += (double)pcl_out.points[i].x + pcl_out.points[i].y + pcl_out.points[i].z + pcl_out.points[i].intensity;
+  }
+  if (std::fabs(sum_in - sum_out) > 1e-6 * std::fabs(sum_in)) { std::printf("undistort identity broken %g %g\n", sum_in, sum_out); return 15; }
+  flb::VoxelGridGpu<PointType> downSizeFilterSurf(&fe);
+  downSizeFilterSurf.setLeafSize(0.5f, 0.5f, 0.5f);       // laserMapping.cpp:2135
+  downSizeFilterSurf.setInputCloud(&pcl_out);              // :2322
+  downSizeFilterSurf.filter(feats_down_body);              // :2323
+  const int feats_down_size = (int)feats_down_body.points.size();
+  if (feats_down_size < 100 || feats_down_size >= (int)lidar.points.size()) return 16;
+  gpu.set_row_mode(flb::LioGpu::EXACT_ROWS);
+  dyn_share_datastruct d3;
+  h_share_model(s, d3);                                    // runs on the filtered scan the front end left on the device
+  if (!d3.valid || d3.h_x.rows() != gpu.effct_feat_num || gpu.effct_feat_num < 50) return 17;
+  state_ikfom ident{};
+  ident.rot.c[3] = 1.0; ident.offset_R_L_I.c[3] = 1.0;
+  if (!fe.to_world(ident, false, world, 1 << 17) || (int)world.points.size() != feats_down_size) return 18;
+  for (int i = 0; i < feats_down_size; ++i)
+    if (world.points[i].x != feats_down_body.points[i].x || world.points[i].intensity != feats_down_body.points[i].intensity) return 19;
+  std::printf("FRONTEND_OK raw=%d down=%d M=%d\n", (int)lidar.points.size(), feats_down_size, gpu.effct_feat_num);
   std::printf("FACADE_OK M=%d deleted=%d map=%d added=%d\n", M, nd, ikdtree.validnum(), added);
   return 0;
 }
