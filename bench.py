@@ -262,33 +262,45 @@ def run_b200(args):
     launches = 0
     npts = 0
     perr = 0.0
+    # the harness keeps its own work out of the timed loop (a C++ caller has none): states/covariances are staged
+    # beforehand, results are inspected afterwards
+    sts = [work["priors"][k].copy() for k in range(W, W + K)]
+    Ps = [P0.copy() for _ in range(K)]
+    dptr = [dev[k].data_ptr() for k in range(W, W + K)]
+    nk = [len(work["scans"][k]) for k in range(W, W + K)]
+    res = [None] * K
+    set_dev, step_ptr = ses.scan_set_device, ses.scan_step_ptr
     e0.record(stream)
-    for k in range(W, W + K):
-        r, st = step_dev(k)
-        launches += r.kernel_launches
-        npts += len(work["scans"][k])
-        perr = max(perr, float(np.linalg.norm(st[:3] - work["truths"][k][:3])))
+    for j in range(K):
+        set_dev(dptr[j], nk[j])
+        res[j] = step_ptr(fov, None, 0, 0, sts[j], Ps[j])
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    for j in range(K):
+        launches += res[j].kernel_launches
+        npts += nk[j]
+        perr = max(perr, float(np.linalg.norm(sts[j][:3] - work["truths"][W + j][:3])))
     # ---------------- timed region 2: host buffers through the C ABI (e2e).  Streaming use of the public API: every
     # step's scan is copied from pinned host memory inside the region (flb_scan_prefetch, overlapping the previous
     # step's kernels) and every step's posterior state / covariance / counters are read back to the host.
     barrier()
-    t0 = time.perf_counter()
-    passes = 0
     k0, k1 = W + K, W + 2 * K
-    ses.scan_prefetch_ptr(pin[k0].data_ptr(), len(work["scans"][k0]), 16)
-    for k in range(k0, k1):
-        st = work["priors"][k].copy()
-        P = P0.copy()
-        ses.scan_step_begin(fov, st, P, True)
-        if k + 1 < k1:
-            ses.scan_prefetch_ptr(pin[k + 1].data_ptr(), len(work["scans"][k + 1]), 16)
-        r = ses.scan_step_finish(fov, st, P)
-        passes += r.update.passes
+    sts2 = [work["priors"][k].copy() for k in range(k0, k1)]
+    Ps2 = [P0.copy() for _ in range(k1 - k0)]
+    pptr = [pin[k].data_ptr() for k in range(k0, k1)] + [0]
+    pn = [len(work["scans"][k]) for k in range(k0, k1)] + [0]
+    res2 = [None] * (k1 - k0)
+    t0 = time.perf_counter()
+    ses.scan_prefetch_ptr(pptr[0], pn[0], 16)
+    for j in range(k1 - k0):
+        ses.scan_step_begin(fov, sts2[j], Ps2[j], True)
+        if j + 1 < k1 - k0:
+            ses.scan_prefetch_ptr(pptr[j + 1], pn[j + 1], 16)
+        res2[j] = ses.scan_step_finish(fov, sts2[j], Ps2[j])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    passes = sum(r.update.passes for r in res2)
     clk = clocks.stop(row_lo, clocks.mark()) if rank == 0 else None
     # ---------------- profiled replay: per-kernel-class CUDA events on the library stream (event timing needs the
     # direct-launch path — no CUDA graph, no side-stream overlap — so it is kept out of the two headline loops)
@@ -405,7 +417,24 @@ def frontend_rows(work, ses, fov, torch, local, W, rank, S=20, leaf=0.5):
         one(i)
     torch.cuda.synchronize()
     t_all = (time.perf_counter() - t0) / S
+    # stage breakdown (wall clock with a synchronisation after every stage: an upper bound per stage, not additive)
+    stage = {"upload_ms": 0.0, "undistort_ms": 0.0, "voxel_filter_ms": 0.0}
+    for i in range(min(S, 8)):
+        t0 = time.perf_counter()
+        fe.upload_ptr(raw[i].data_ptr(), raw[i].shape[0])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        fe.undistort(poses[i], ends[i])
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        fe.voxel_filter(leaf)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        stage["upload_ms"] += 1e3 * (t1 - t0) / min(S, 8)
+        stage["undistort_ms"] += 1e3 * (t2 - t1) / min(S, 8)
+        stage["voxel_filter_ms"] += 1e3 * (t3 - t2) / min(S, 8)
     out = {"what": "raw scan (host, 48-B PointType) -> undistort -> VoxelGrid -> update -> map_incremental; wall clock, host buffers",
+           "stages_synced": stage,
            "leaf": leaf, "raw_points_mean": float(np.mean([r.shape[0] for r in raw])), "down_points_mean": float(np.mean(nd)),
            "front_ms_per_scan": 1e3 * t_front, "scans_per_s_raw_to_posterior": 1.0 / t_all, "samples": S,
            "h2d_bytes_per_scan": int(48 * np.mean([r.shape[0] for r in raw]))}

@@ -332,7 +332,7 @@ __global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage, int
   const int n = (int)stage[26 + NDOF * NDOF];
   for (int i = threadIdx.x; i < NDOF * NDOF; i += blockDim.x) { c->Pp[i] = P0[i]; c->P[i] = P0[i]; }
   if (threadIdx.x < 26) { c->x[threadIdx.x] = x0[threadIdx.x]; c->xp[threadIdx.x] = x0[threadIdx.x]; }
-  if (threadIdx.x >= 32 && threadIdx.x < 40) work_counts[threadIdx.x - 32] = 0;   // per-pass k-NN work-list counters
+  if (threadIdx.x >= 32 && threadIdx.x < 48) work_counts[threadIdx.x - 32] = 0;   // per-pass k-NN work-list counters [0..7] + tickets [8..15]
   __syncthreads();
   if (threadIdx.x == 0) {
     c->it = -1; c->t = 0; c->converge = 1; c->finished = 0; c->need_host = 0; c->passes = 0; c->searches = 0;

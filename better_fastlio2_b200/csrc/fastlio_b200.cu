@@ -195,7 +195,7 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   rc |= dev_alloc(m, (void**)&d.cbits, sizeof(uint64_t) * 8 * (size_t)m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.clist, sizeof(uint32_t) * (size_t)m->chash_cap);
   rc |= dev_alloc(m, (void**)&d.counters, sizeof(int) * CNT_COUNT);
-  rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 32);   // [0..3] counts, [4..9] range, [12] work count, [16..23] per-pass work counts
+  rc |= dev_alloc(m, (void**)&m->d_misc, sizeof(int) * 32);   // [0..3] counts, [4..9] range, [12] work count, [13] ticket, [16..23] per-pass work counts, [24..31] per-pass tickets
   rc |= dev_alloc(m, (void**)&m->d_phase, sizeof(int) * 8);
   if (rc) { flb_map_destroy(m); return 1; }
   if (cudaMallocHost((void**)&m->h_counters, sizeof(int) * CNT_COUNT) != cudaSuccess) { flb_map_destroy(m); return set_err("cudaMallocHost failed"); }
@@ -442,7 +442,8 @@ static int launch_knn(flb_map* m, KnnArgs a) {
   if (a.stride <= 0) a.stride = a.n;
   if (!a.work_count) {   // (device-driven scans use per-pass counters zeroed by k_esikf_begin: no memset node per pass)
     a.work_count = m->d_misc + 12;
-    CU(cudaMemsetAsync(a.work_count, 0, sizeof(int), m->stream));
+    a.work_ticket = m->d_misc + 13;
+    CU(cudaMemsetAsync(a.work_count, 0, 2 * sizeof(int), m->stream));
   }
   k_knn_stencil<K><<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
   // the fallback grid is sized for the typical <2 % unresolved share; it loops over the list
@@ -1071,7 +1072,7 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
       KnnArgs a;
       a.m = m->d; a.q = nullptr; a.n = cap; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
       a.phase_stats = m->prof_on ? m->d_phase : nullptr;
-      a.ctl = s->ctl; a.body = s->body; a.stride = cap; a.work_count = p < 8 ? m->d_misc + 16 + p : nullptr;
+      a.ctl = s->ctl; a.body = s->body; a.stride = cap; a.work_count = p < 8 ? m->d_misc + 16 + p : nullptr; a.work_ticket = p < 8 ? m->d_misc + 24 + p : nullptr;
       if (launch_knn<5>(m, a)) return 1;
     }
     {

@@ -115,12 +115,22 @@ __device__ __forceinline__ int warp_merge(TopK<K>& t, unsigned gmask, int gl, in
   return gcount;
 }
 
-// 64-bit voxel mask of a 4x4x4 block (slot order s = (z*4 + y)*4 + x) from three 4-bit per-axis masks
+// 64-bit voxel mask of a 4x4x4 block (slot order s = (z*4 + y)*4 + x) from three 4-bit per-axis masks.  The mask is
+// separable: (x pattern) & (y pattern) & (z pattern), each built with a multiply that replicates a small bit group
+// (no carries: the replicated groups never overlap), on 32-bit halves (z = 0,1 | z = 2,3).
+__device__ __forceinline__ unsigned xpat32(unsigned xm) { return xm * 0x11111111u; }   // xm in every nibble
+__device__ __forceinline__ unsigned ypat32(unsigned ym) {                              // nibble y of every 16-bit group
+  const unsigned sp = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);   // bit y -> bit 4y
+  return (sp * 0xFu) * 0x00010001u;
+}
+__device__ __forceinline__ unsigned zpat32(unsigned z2) {   // two z bits of one half: bit 0 -> low 16 bits, bit 1 -> high 16
+  return (0u - (z2 & 1u)) & 0x0000FFFFu | (0u - ((z2 >> 1) & 1u)) & 0xFFFF0000u;
+}
+__device__ __forceinline__ unsigned long long mask_from_xy(unsigned xy, unsigned zm) {
+  return ((unsigned long long)(xy & zpat32(zm >> 2)) << 32) | (unsigned long long)(xy & zpat32(zm & 3u));
+}
 __device__ __forceinline__ unsigned long long mask_from_axes(unsigned xm, unsigned ym, unsigned zm) {
-  const unsigned row = ((ym & 1u) ? xm : 0u) | ((ym & 2u) ? xm << 4 : 0u) | ((ym & 4u) ? xm << 8 : 0u) | ((ym & 8u) ? xm << 12 : 0u);
-  const unsigned lo = ((zm & 1u) ? row : 0u) | ((zm & 2u) ? row << 16 : 0u);
-  const unsigned hi = ((zm & 4u) ? row : 0u) | ((zm & 8u) ? row << 16 : 0u);
-  return ((unsigned long long)hi << 32) | lo;
+  return mask_from_xy(xpat32(xm) & ypat32(ym), zm);
 }
 // voxels of block (bx,by,bz) that lie inside the 5x5x5 stencil around voxel (cvx,cvy,cvz)
 __device__ __forceinline__ unsigned axis_in_stencil(int b, int cv) {
@@ -191,6 +201,7 @@ struct KnnArgs {
   int* phase_stats;    // optional [4]: queries finishing in phase A / B / C, total candidate points
   int* worklist;       // stencil kernel: indices of queries it could not prove complete; warp kernel: its input list
   int* work_count;     // number of entries in worklist (device)
+  int* work_ticket;    // exact kernel: next unclaimed work-list entry (device, zeroed with work_count)
   const EsikfCtl* ctl; // device-driven mode: queries = body_to_world(ctl->pose, body[i]); skipped unless a search pass
   const float4* body;
   int stride;          // leading dimension of nbr (>= n; the session capacity, so launches do not depend on n)
@@ -449,14 +460,19 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
   const int lane = threadIdx.x & 31;
   const int g = lane / G, gl = lane - g * G, gbase = g * G;
   const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << gbase);
-  const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   const float ds = m.ds;
   const float lim = a.max_d2;
   FLB_TRACE_BEGIN(3 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
   const int nwork = *a.work_count;
-  for (int wb = warp_id * QPW; wb < nwork; wb += warps_per_grid * QPW) {   // warp-uniform trip count
+  // Dynamic distribution: every warp claims the next QPW list entries with one atomic.  Query cost varies by two orders
+  // of magnitude (ring 1 vs ring 3, dense vs empty blocks), so a static stride leaves the kernel waiting for the warp
+  // that happened to draw several expensive queries.
+  for (;;) {
+    int wb = 0;
+    if (lane == 0) wb = atomicAdd(a.work_ticket, QPW);
+    wb = __shfl_sync(FULL, wb, 0);
+    if (wb >= nwork) break;   // warp-uniform
     const int w = wb + g;
     const bool active = w < nwork;
     int i = 0;
@@ -630,14 +646,19 @@ __device__ __forceinline__ unsigned long long stencil_mask(unsigned ax, unsigned
   return mask_from_axes((ax >> ((b & 1) << 2)) & 15u, (ay >> (((b >> 1) & 1) << 2)) & 15u, (az >> ((b >> 2) << 2)) & 15u);
 }
 
-// Per-thread shared-memory columns of the stencil kernel: 188 B per query, so that 7 CTAs of 128 threads (the register
+// Per-thread shared-memory columns of the stencil kernel: 204 B per query, so that 7 CTAs of 128 threads (the register
 // limit) fit one SM and a 120k-point scan is a single wave on 148 SMs.
 struct StencilSmem {
   int blk[8][STENCIL_THREADS];                     // block index of the 8 probed blocks (-1: absent)
   unsigned long long c5[8][STENCIL_THREADS];       // occupied voxels of each block inside the 5x5x5 stencil
   float gap[15][STENCIL_THREADS];                  // squared query-to-slab gaps: x[5], y[5], z[5]
   unsigned char list[SHELL_LIST][STENCIL_THREADS]; // surviving shell voxels, stencil-relative index jx + 5 jy + 25 jz
+  unsigned xy3[4][STENCIL_THREADS];                // x&y pattern of the inner 3x3x3 mask per (x half, y half) of the 8 blocks
 };
+// inner 3x3x3 mask of block half b (dynamic b): one shared-memory word + the z pattern of that half
+__device__ __forceinline__ unsigned long long inner_mask(const StencilSmem& sm, int tid, unsigned iz, int b) {
+  return mask_from_xy(sm.xy3[b & 3][tid], (iz >> ((b >> 2) << 2)) & 15u);
+}
 
 // Visit the candidate voxels (c5 & inner mask, or c5 & ~inner mask when OUTER) of the 8 blocks: per-thread cursor over
 // the blocks, four independent 16-B point loads in flight, branch-free insertion.
@@ -654,7 +675,7 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const StencilSmem&
       pid[u] = 0u;
       while (cand == 0ull && b < 7) {
         ++b;
-        const unsigned long long in3 = stencil_mask(ix, iy, iz, b);
+        const unsigned long long in3 = inner_mask(sm, tid, iz, b);
         cand = sm.c5[b][tid] & (OUTER ? ~in3 : in3);
         blk = sm.blk[b][tid];
       }
@@ -701,7 +722,7 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem&
     int b = -1;
     unsigned long long cand = 0ull;
     for (;;) {
-      while (cand == 0ull && b < 7) { ++b; cand = sm.c5[b][tid] & ~stencil_mask(ix, iy, iz, b); }
+      while (cand == 0ull && b < 7) { ++b; cand = sm.c5[b][tid] & ~inner_mask(sm, tid, iz, b); }
       if (cand == 0ull) break;
       const int sl = __ffsll((long long)cand) - 1;
       cand &= cand - 1;
@@ -807,6 +828,8 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
       sm.blk[b][tid] = blk8[b];
       sm.c5[b][tid] = occ[b] & stencil_mask(ax5, ay5, az5, b);
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sm.xy3[q][tid] = xpat32((ix >> ((q & 1) << 2)) & 15u) & ypat32((iy >> ((q >> 1) << 2)) & 15u);
     // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
     stencil_pass<K, false>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);

@@ -7,7 +7,7 @@ mkdir -p $OUT
 echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 tail -15 $OUT/${TAG}_pytest.log
 for kv in "$@"; do
-  name=$(echo "$kv" | tr '= ' '__')
+  name=$(echo "$kv" | tr '= /.' '____')
   env $kv timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_${name}.json 2> $OUT/${TAG}_bench_${name}.err
   echo "$kv: $(python -c "import json,sys; d=json.load(open('$OUT/${TAG}_bench_${name}.json')); print(d['value'], d['e2e']['value'], d['kernel_ms_per_step'])")"
 done
