@@ -398,9 +398,7 @@ def frontend_rows(work, ses, fov, torch, local, W, rank, S=20, leaf=0.5):
     P0 = work["P"]
 
     def one(i, with_step=True):
-        fe.upload_ptr(raw[i].data_ptr(), raw[i].shape[0])
-        fe.undistort(poses[i], ends[i])
-        n = fe.voxel_filter(leaf)
+        n = fe.process_ptr(raw[i].data_ptr(), raw[i].shape[0], poses[i], ends[i], leaf)
         if with_step:
             st, P = work["priors"][ks[i]].copy(), P0.copy()
             ses.scan_step_ptr(fov, None, 0, 0, st, P)

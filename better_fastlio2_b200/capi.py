@@ -77,7 +77,7 @@ EXPORTS = [
     "flb_neighbors_download", "flb_fov_segment", "flb_scan_step", "flb_session_stream", "flb_session_sync",
     "flb_map_profile_enable", "flb_map_profile_read", "flb_session_set_update_engine", "flb_scan_prefetch", "flb_scan_step_begin", "flb_scan_step_finish",
     "flb_frontend_create", "flb_frontend_destroy", "flb_frontend_upload", "flb_frontend_undistort",
-    "flb_frontend_voxel_filter", "flb_frontend_download_undistorted", "flb_frontend_download_down",
+    "flb_frontend_voxel_filter", "flb_frontend_process", "flb_frontend_download_undistorted", "flb_frontend_download_down",
     "flb_frontend_points_to_world", "flb_voxel_grid_filter", "flb_map_reconstruct_keyframes",
 ]
 
@@ -140,6 +140,7 @@ def lib():
         L.flb_frontend_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.flb_frontend_undistort.argtypes = [vp, dp, C.c_int, dp]
         L.flb_frontend_voxel_filter.argtypes = [vp, C.c_float, ip]
+        L.flb_frontend_process.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, C.c_float, ip]
         L.flb_frontend_download_undistorted.argtypes = [vp, fp, fp, vp, C.c_int, ip]
         L.flb_frontend_download_down.argtypes = [vp, fp, fp, C.c_int, ip]
         L.flb_frontend_points_to_world.argtypes = [vp, C.c_int, dp, fp, C.c_int, ip]
@@ -476,6 +477,15 @@ class FrontEnd:
         _chk(lib().flb_frontend_voxel_filter(self.h, float(leaf), C.byref(n)))
         self.session.n = n.value
         return n.value
+
+    def process_ptr(self, ptr, n, imu_poses, state26_end, leaf, stride=POINT_STRIDE, off_i=OFF_INTENSITY, off_c=OFF_CURVATURE):
+        """flb_frontend_process on a raw host pointer; imu_poses must already be a C-contiguous (k,22) float64 array."""
+        cnt = C.c_int(0)
+        _chk(lib().flb_frontend_process(self.h, C.c_void_p(ptr), int(n), stride, off_i, off_c, _p(imu_poses), len(imu_poses),
+                                        _p(state26_end), float(leaf), C.byref(cnt)))
+        self.n_raw = int(n)
+        self.session.n = cnt.value
+        return cnt.value
 
     def download_undistorted(self):
         n = self.n_raw

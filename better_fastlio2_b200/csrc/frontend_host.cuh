@@ -217,6 +217,14 @@ extern "C" int flb_frontend_voxel_filter(flb_frontend* f, float leaf, int* n_out
   return scan_reset(s, nd);
 }
 
+// upload + undistort + voxel filter in one call (one synchronisation): meas.lidar -> feats_down_body on the device
+extern "C" int flb_frontend_process(flb_frontend* f, const void* pts, int n, int stride, int off_intensity, int off_curvature,
+                                    const double* imu_poses22, int n_poses, const double* state26_end, float leaf, int* n_out) {
+  if (flb_frontend_upload(f, pts, n, stride, off_intensity, off_curvature)) return 1;
+  if (imu_poses22 && n_poses > 0 && flb_frontend_undistort(f, imu_poses22, n_poses, state26_end)) return 1;
+  return flb_frontend_voxel_filter(f, leaf, n_out);
+}
+
 static int fe_download(flb_map* m, const float4* src, const float* src_curv, int n, float* out_xyzi, float* out_curv, int cap) {
   const int c = std::min(n, cap);
   if (c > 0 && out_xyzi) CU(cudaMemcpyAsync(out_xyzi, src, sizeof(float4) * (size_t)c, cudaMemcpyDeviceToHost, m->stream));

@@ -244,6 +244,10 @@ int flb_frontend_undistort(flb_frontend* f, const double* imu_poses, int n_poses
  * PCL's int32 overflow guard returns the input unchanged).  The result becomes the session's current scan
  * (as flb_scan_upload would); *n_out = feats_down_size.  Sums run in time order inside a leaf (PCL: unspecified). */
 int flb_frontend_voxel_filter(flb_frontend* f, float leaf_size, int* n_out);
+/* The three calls above in one (one synchronisation): raw scan in, feats_down_body left on the device as the session's
+ * current scan.  imu_poses == NULL or n_poses == 0 skips the undistortion (no IMU / already compensated). */
+int flb_frontend_process(flb_frontend* f, const void* pts, int n, int stride_bytes, int off_intensity, int off_curvature,
+                         const double* imu_poses, int n_poses, const double* state26_end, float leaf_size, int* n_out);
 /* Read back feats_undistort (x,y,z,intensity per point; curvature; perm[j] = upload index of sorted point j) and
  * feats_down_body.  Any output pointer may be NULL; at most cap points are written, *n = the cloud size. */
 int flb_frontend_download_undistorted(flb_frontend* f, float* out_xyzi, float* out_curvature, int* out_perm, int cap, int* n);

@@ -115,6 +115,24 @@ def test_undistort_then_filter_and_publish(raw, rig, oracle):
     assert np.array_equal(w1, oracle.body_to_world4(st, und))
 
 
+def test_process_one_call_equals_three(raw, rig):
+    tree, ses, fe = rig
+    fe.upload(raw["pts48"])
+    fe.undistort(raw["poses"], raw["end"])
+    n3 = fe.voxel_filter(0.5)
+    a, ac = fe.download_down()
+    buf = np.ascontiguousarray(raw["pts48"])
+    poses = np.ascontiguousarray(raw["poses"], np.float64)
+    end = np.ascontiguousarray(raw["end"], np.float64)
+    n1 = fe.process_ptr(buf.ctypes.data, len(buf), poses, end, 0.5)
+    b, bc = fe.download_down()
+    assert n1 == n3 and np.array_equal(a, b) and np.array_equal(ac, bc)
+    # without IMU poses the scan is only filtered (upload order)
+    n0 = fe.process_ptr(buf.ctypes.data, len(buf), np.zeros((0, 22)), end, 0.5)
+    und, _, perm = fe.download_undistorted()
+    assert np.array_equal(perm, np.arange(len(buf))) and np.array_equal(und[:, :3], raw["xyz"]) and n0 > 0
+
+
 def test_raw_scan_pipeline_pose_parity(raw, rig, oracle):
     """meas.lidar -> UndistortPcl -> VoxelGrid -> update -> map_incremental on the GPU vs the same chain on the oracle."""
     tree, ses, fe = rig
