@@ -293,11 +293,16 @@ def run_b200(args):
     res2 = [None] * (k1 - k0)
     t0 = time.perf_counter()
     ses.scan_prefetch_ptr(pptr[0], pn[0], 16)
+    lat = np.empty(k1 - k0)
+    tp = t0
     for j in range(k1 - k0):
         ses.scan_step_begin(fov, sts2[j], Ps2[j], True)
         if j + 1 < k1 - k0:
             ses.scan_prefetch_ptr(pptr[j + 1], pn[j + 1], 16)
         res2[j] = ses.scan_step_finish(fov, sts2[j], Ps2[j])
+        tn = time.perf_counter()
+        lat[j] = tn - tp    # posterior-to-posterior period of the streaming loop (host clock)
+        tp = tn
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     passes = sum(r.update.passes for r in res2)
@@ -345,6 +350,9 @@ def run_b200(args):
                                     "+ a new scan every step",
                        "pose_err_vs_truth_max_m": perr},
             "gpu_launches": launches,
+            "latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3),
+                           "max": float(lat.max() * 1e3), "what": "per-scan period of the e2e loop (host buffers, host clock)"},
+            "device_bytes": int(stats.get("device_bytes", 0)),
             "e2e": {"value": aggregate_scans_per_s(world_size, K, e2e_ms_max), "unit": "scans/s",
                     "h2d_bytes_per_step": int(16 * n_mean), "d2h_bytes_per_step": int(passes / K * 93 * 8 + 2 * 128 + 8)},
             "roofline": {"bound": "hbm", "kernel": "k_knn<5> (5-NN search pass)", "achieved": achieved, "peak": peak,

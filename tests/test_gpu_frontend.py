@@ -8,6 +8,8 @@ Tolerances (floating point rows):
   * voxel grid: bit-exact against the oracle summing in the same (stable) order; <= 1e-3 against the PCL std::sort
     order (float sums of <= a few dozen coordinates up to ~100 m);
   * pipeline: posterior pose within 1e-4 m / 1e-4 rad of the oracle pipeline (BASELINE.json north_star)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -223,3 +225,22 @@ def test_reconstruct_keyframes(raw, oracle):
     none = capi.reconstruct_keyframes(tree, [], np.zeros((0, 6), np.float32), leaf)
     assert len(none) == 0 and tree.validnum() == 0
     tree.close()
+
+
+def test_frontend_golden_fixture(rig):
+    """GPU path vs the committed fixture tests/golden/frontend/frontend_mini.npz (no oracle call needed on the box)."""
+    tree, ses, fe = rig
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend", "frontend_mini.npz"))
+    fe.upload(capi.pack_pointtype(g["xyz"], g["intensity"], g["curvature"]))
+    fe.undistort(g["poses"], g["end"])
+    und, cur, perm = fe.download_undistorted()
+    g_by_in = np.empty_like(g["xyz"])
+    o_by_in = np.empty_like(g["xyz"])
+    g_by_in[perm] = und[:, :3]
+    o_by_in[g["perm"]] = g["undistorted"]
+    assert _ulp_close(g_by_in, o_by_in).all()
+    n = fe.voxel_filter(float(g["leaf"]))
+    d, dc = fe.download_down()
+    assert abs(n - len(g["down_stable"])) <= 2                    # a 1-ulp difference may move a point across a leaf face
+    if n == len(g["down_stable"]):
+        assert np.abs(d - g["down_stable"]).max() < 1e-3 and np.abs(d - g["down_pcl"]).max() < 1e-3

@@ -1,6 +1,8 @@
 """CPU tests: the front-end oracle (oracle/frontend_oracle.cpp — UndistortPcl backward pass, pcl::VoxelGrid, the key-frame
 transform, pointBodyToWorld) cross-validated against independent numpy/scipy implementations.  These rows are "parity
 unpinned" (the reference ships no vectors and needs Eigen/PCL, absent here); this is the strongest pin available."""
+import os
+
 import numpy as np
 import pytest
 from scipy.spatial.transform import Rotation as Rot
@@ -148,3 +150,19 @@ def test_body_to_world4_matches_scipy(raw, oracle):
     ref = synth.body_to_world_np(st, p4[:, :3])
     assert np.abs(out[:, :3] - ref).max() < 1e-4
     assert np.array_equal(out[:, 3], p4[:, 3])
+
+
+GOLD_FE = os.path.join(os.path.dirname(__file__), "golden", "frontend", "frontend_mini.npz")
+
+
+def test_oracle_reproduces_frontend_golden(oracle):
+    """The committed fixture (tests/golden/make_golden_frontend.py) pins the front-end oracle against drift."""
+    g = np.load(GOLD_FE)
+    und, perm = oracle.undistort(g["xyz"], g["curvature"], g["poses"], g["end"])
+    assert np.array_equal(perm, g["perm"]) and np.array_equal(und, g["undistorted"])
+    p4 = np.column_stack([und, g["intensity"][perm]]).astype(np.float32)
+    for order, key in (("pcl", "down_pcl"), ("stable", "down_stable")):
+        d, dc, ovf = oracle.voxel_grid(p4, float(g["leaf"]), curvature=g["curvature"][perm], order=order)
+        assert not ovf and np.array_equal(d, g[key]) and np.array_equal(dc, g[key + "_curv"])
+    assert np.array_equal(oracle.transform_cloud_rpy(p4, g["pose6"]), g["transformed"])
+    assert np.array_equal(oracle.body_to_world4(g["end"], g["down_stable"]), g["world"])
