@@ -811,8 +811,9 @@ extern "C" int flb_scan_upload(flb_session* s, const float* xyz, int n, int stri
       if (bytes > s->raw_cap) {
         if (s->raw) cudaFree(s->raw);
         s->raw = nullptr; s->raw_cap = 0;
-        CU(cudaMalloc((void**)&s->raw, std::max(bytes, (size_t)1 << 20)));
-        s->raw_cap = std::max(bytes, (size_t)1 << 20);
+        const size_t rc = std::max(bytes, (size_t)s->cap * (size_t)stride);   // sized once for the session capacity
+        CU(cudaMalloc((void**)&s->raw, rc));
+        s->raw_cap = rc;
       }
       CU(cudaMemcpyAsync(s->raw, xyz, bytes, cudaMemcpyHostToDevice, m->stream));
       k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(s->raw, stride, s->body, n);

@@ -151,7 +151,7 @@ extern "C" int flb_frontend_upload(flb_frontend* f, const void* pts, int n, int 
   if (bytes > f->raw_cap) {
     if (f->raw) cudaFree(f->raw);
     f->raw = nullptr; f->raw_cap = 0;
-    const size_t cap = std::max(bytes, (size_t)f->cap * 16);
+    const size_t cap = std::max(bytes, (size_t)f->cap * (size_t)stride);   // sized once for the capacity: scans vary in size
     CU(cudaMalloc((void**)&f->raw, cap));
     f->raw_cap = cap;
   }

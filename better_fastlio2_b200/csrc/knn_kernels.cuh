@@ -335,6 +335,32 @@ __device__ __forceinline__ void group_scan_blocks(const MapDev& m, unsigned gmas
         mm &= ~block_stencil_mask(qbx + (off & 15) - 8, qby + ((off >> 4) & 15) - 8, qbz + (off >> 8) - 8, cvx, cvy, cvz);
       if (u == 0) { c0 = mm; b0 = blk; } else { c1 = mm; b1 = blk; }
     }
+    if constexpr (G == 32) {
+      // a whole warp per query: lane gl owns exactly the slots gl and gl+32 of each block, so the (at most) four
+      // candidates of this step sit at fixed positions — no bit scanning, four independent predicated loads
+      bool ok[4];
+      unsigned pid[4];
+      ok[0] = ((unsigned)c0 >> gl) & 1u; ok[1] = ((unsigned)(c0 >> 32) >> gl) & 1u;
+      ok[2] = ((unsigned)c1 >> gl) & 1u; ok[3] = ((unsigned)(c1 >> 32) >> gl) & 1u;
+      pid[0] = (unsigned)b0 * 64u + (unsigned)gl; pid[1] = pid[0] + 32u;
+      pid[2] = (unsigned)b1 * 64u + (unsigned)gl; pid[3] = pid[2] + 32u;
+      float4 e[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (ok[v]) e[v] = __ldg(&m.slots[pid[v]]);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (ok[v]) {
+          const float4 p = e[v];
+          const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
+          if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
+          walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
+            const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+            if (d2 <= limit) t.insert(d2, o.x, o.y, o.z);
+          });
+        }
+      }
+    } else
     for (;;) {   // per-lane candidate loop (ordinary SIMT masking: lanes drop out as they run dry)
       unsigned pid[4];
       int nc = 0;
@@ -517,6 +543,15 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       if (!__any_sync(FULL, !done)) break;
       const bool go = !done;
       const int wd = 2 * r + 1, nb = wd * wd * wd;
+      // A query that has no k-th distance yet cannot prune anything, and a shell that cuts through a dense surface then
+      // costs hundreds of candidate insertions (the kernel's tail).  Such a query visits the shell in two halves: the
+      // blocks nearer than r block edges first, a merge, then the farther ones — now bounded by the k-th distance just
+      // found, which usually prunes them all before a single probe.
+      const bool need_split = go && gcount < K;
+      const int nhalf = __any_sync(FULL, need_split) ? 2 : 1;    // warp-uniform
+      const float dsplit = need_split ? (float)(r * r) * bs4 * bs4 : CUDART_INF_F;
+#pragma unroll 1
+      for (int half = 0; half < nhalf; ++half) {
       const float bound = gcount == K ? thr : CUDART_INF_F;
 #pragma unroll 1
       for (int base = 0; base < nb; base += 4 * G) {
@@ -534,7 +569,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
               const int bx = qbx + dx, by = qby + dy, bz = qbz + dz;
               const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
               const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);
-              if (!(md > bound || md > lim)) {
+              if (!(md > bound || md > lim) && (half == 0 ? md <= dsplit : md > dsplit)) {
                 off[u] = (dx + 8) | ((dy + 8) << 4) | ((dz + 8) << 8);
                 ent[u] = __ldg(reinterpret_cast<const uint4*>(&m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask]));
               }
@@ -560,6 +595,11 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
           group_scan_blocks<K, G>(m, gmask, gbase, todo, blk[u], mask[u], off[u], qbx, qby, qbz, gl, qx, qy, qz, cvx, cvy, cvz,
                                   r == 1, fminf(lim, bound), t);
         }
+      }
+      if (half + 1 < nhalf) {   // intermediate merge: gives the far half its bound
+        const int gc = warp_merge<K>(t, gmask, gl, lane, rd, rx, ry, rz, thr);
+        if (go) gcount = gc;
+      }
       }
       {
         // merge (all groups together; for a finished group it reproduces its result)
@@ -646,7 +686,7 @@ __device__ __forceinline__ unsigned long long stencil_mask(unsigned ax, unsigned
   return mask_from_axes((ax >> ((b & 1) << 2)) & 15u, (ay >> (((b >> 1) & 1) << 2)) & 15u, (az >> ((b >> 2) << 2)) & 15u);
 }
 
-// Per-thread shared-memory columns of the stencil kernel: 204 B per query, so that 7 CTAs of 128 threads (the register
+// Per-thread shared-memory columns of the stencil kernel: 220 B per query, so that 7 CTAs of 128 threads (the register
 // limit) fit one SM and a 120k-point scan is a single wave on 148 SMs.
 struct StencilSmem {
   int blk[8][STENCIL_THREADS];                     // block index of the 8 probed blocks (-1: absent)
@@ -654,10 +694,13 @@ struct StencilSmem {
   float gap[15][STENCIL_THREADS];                  // squared query-to-slab gaps: x[5], y[5], z[5]
   unsigned char list[SHELL_LIST][STENCIL_THREADS]; // surviving shell voxels, stencil-relative index jx + 5 jy + 25 jz
   unsigned xy3[4][STENCIL_THREADS];                // x&y pattern of the inner 3x3x3 mask per (x half, y half) of the 8 blocks
+  unsigned z3[4][STENCIL_THREADS];                 // z pattern of the inner mask: [z half of the block pair * 2 + word (lo, hi)]
 };
-// inner 3x3x3 mask of block half b (dynamic b): one shared-memory word + the z pattern of that half
-__device__ __forceinline__ unsigned long long inner_mask(const StencilSmem& sm, int tid, unsigned iz, int b) {
-  return mask_from_xy(sm.xy3[b & 3][tid], (iz >> ((b >> 2) << 2)) & 15u);
+// inner 3x3x3 mask of block half b (dynamic b): three shared-memory words, two ANDs
+__device__ __forceinline__ unsigned long long inner_mask(const StencilSmem& sm, int tid, int b) {
+  const unsigned xy = sm.xy3[b & 3][tid];
+  const int zq = (b >> 2) << 1;
+  return ((unsigned long long)(xy & sm.z3[zq + 1][tid]) << 32) | (unsigned long long)(xy & sm.z3[zq][tid]);
 }
 
 // Visit the candidate voxels (c5 & inner mask, or c5 & ~inner mask when OUTER) of the 8 blocks: per-thread cursor over
@@ -675,7 +718,7 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const StencilSmem&
       pid[u] = 0u;
       while (cand == 0ull && b < 7) {
         ++b;
-        const unsigned long long in3 = inner_mask(sm, tid, iz, b);
+        const unsigned long long in3 = inner_mask(sm, tid, b);
         cand = sm.c5[b][tid] & (OUTER ? ~in3 : in3);
         blk = sm.blk[b][tid];
       }
@@ -722,7 +765,7 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem&
     int b = -1;
     unsigned long long cand = 0ull;
     for (;;) {
-      while (cand == 0ull && b < 7) { ++b; cand = sm.c5[b][tid] & ~inner_mask(sm, tid, iz, b); }
+      while (cand == 0ull && b < 7) { ++b; cand = sm.c5[b][tid] & ~inner_mask(sm, tid, b); }
       if (cand == 0ull) break;
       const int sl = __ffsll((long long)cand) - 1;
       cand &= cand - 1;
@@ -829,7 +872,10 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
       sm.c5[b][tid] = occ[b] & stencil_mask(ax5, ay5, az5, b);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sm.xy3[q][tid] = xpat32((ix >> ((q & 1) << 2)) & 15u) & ypat32((iy >> ((q >> 1) << 2)) & 15u);
+    for (int q = 0; q < 4; ++q) {
+      sm.xy3[q][tid] = xpat32((ix >> ((q & 1) << 2)) & 15u) & ypat32((iy >> ((q >> 1) << 2)) & 15u);
+      sm.z3[q][tid] = zpat32((((iz >> ((q >> 1) << 2)) & 15u) >> ((q & 1) << 1)) & 3u);
+    }
     // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
     stencil_pass<K, false>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);

@@ -14,4 +14,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_b.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_knn_stencil|k_residual|k_knn' -s 12 -c 6 \
     -o $OUT/${TAG}_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_f.log 2>&1
+if [ -f better_fastlio2_b200/libfastlio_b200_trace.so ]; then
+  FLB_LIB=better_fastlio2_b200/libfastlio_b200_trace.so timeout 300 python tools/trace_step.py --steps 20 --out $OUT/${TAG}_trace.json > $OUT/${TAG}_trace.txt 2>&1
+fi
 tail -3 $OUT/${TAG}_pytest.log; cat $OUT/${TAG}_smoke.log | tail -2; cat $OUT/${TAG}_bench.json
