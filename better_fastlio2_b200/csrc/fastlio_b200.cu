@@ -97,6 +97,7 @@ struct flb_map {
   int* d_phase = nullptr;        // k-NN phase histogram (device, 4 ints)
   int* worklist = nullptr;       // unresolved-query list of the stencil k-NN kernel
   int work_cap = 0;
+  bool scratch_clean = false;    // the downsample scratch hash was already cleared off the critical path (scan graph)
   int knn_group = 32;            // lanes per query of the exact k-NN kernel: a whole warp (measured 2557 vs 2251 scans/s for 8,
                                  // profiles/r1d_*); FLB_KNN_GROUP=8 selects four queries per warp (tuning only)
 };
@@ -305,8 +306,11 @@ static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls
   if (mode == 1 || mode == 2) {
     if (ensure_scratch(m, n)) return 1;
     const uint32_t sc = next_pow2((uint64_t)std::max(n, 512) * 2);
-    CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
-    CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
+    if (!m->scratch_clean) {
+      CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
+      CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
+    }
+    m->scratch_clean = false;
     k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
     k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
     m->launches += 2;
@@ -1061,6 +1065,16 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
       CU(cudaStreamWaitEvent(s->side, s->ev_fork[p], 0));
       if (md12) k_esikf_pre<12><<<1, dev::ESIKF_THREADS, 0, s->side>>>(s->ctl, s->d_scr);
       else k_esikf_pre<6><<<1, dev::ESIKF_THREADS, 0, s->side>>>(s->ctl, s->d_scr);
+      if (p == 0 && with_insert) {
+        // the insert's scratch hash and counters are cleared here, next to the first pass, instead of between the
+        // insert kernels at the end of the scan (three memset nodes off the critical path)
+        if (!m->capturing && ensure_scratch(m, cap)) return 1;
+        const uint32_t sc = next_pow2((uint64_t)std::max(cap, 512) * 2);
+        CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, s->side));
+        CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, s->side));
+        CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, s->side));
+        m->scratch_clean = true;
+      }
       CU(cudaEventRecord(s->ev_join[p], s->side));
     } else {
       ProfScope ps(m, FLB_K_REDUCE);
@@ -1183,7 +1197,7 @@ static int enqueue_map_incremental(flb_session* s, const double* state26, int fl
   const int n = s->n;
   if (n <= 0 && !from_ctl) return 0;
   const PoseDev pose = from_ctl ? PoseDev{} : pose_from(state26);
-  CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
+  if (!m->scratch_clean) CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
   {
     ProfScope ps(m, FLB_K_CLASSIFY);
     k_classify<<<grid_for(from_ctl ? s->cap : n, 256, m->sm_count * 8), 256, 0, st>>>(pose, from_ctl ? s->ctl : nullptr, s->body, s->nbr, s->cnt, n, s->cap,

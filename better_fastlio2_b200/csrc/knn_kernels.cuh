@@ -12,6 +12,7 @@
 // Completeness test: have k candidates and d_k < (distance from the query to the boundary of the searched region)^2.
 // Roofline: HBM/L2-latency bound gather; algorithmic bytes 16 (query) + 80 (5 neighbours) + 80 (cache write).
 #pragma once
+#include "mask_bits.h"
 #include "voxel_map.cuh"
 #include <math_constants.h>
 
@@ -115,33 +116,13 @@ __device__ __forceinline__ int warp_merge(TopK<K>& t, unsigned gmask, int gl, in
   return gcount;
 }
 
-// 64-bit voxel mask of a 4x4x4 block (slot order s = (z*4 + y)*4 + x) from three 4-bit per-axis masks.  The mask is
-// separable: (x pattern) & (y pattern) & (z pattern), each built with a multiply that replicates a small bit group
-// (no carries: the replicated groups never overlap), on 32-bit halves (z = 0,1 | z = 2,3).
-__device__ __forceinline__ unsigned xpat32(unsigned xm) { return xm * 0x11111111u; }   // xm in every nibble
-__device__ __forceinline__ unsigned ypat32(unsigned ym) {                              // nibble y of every 16-bit group
-  const unsigned sp = (ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9);   // bit y -> bit 4y
-  return (sp * 0xFu) * 0x00010001u;
-}
-__device__ __forceinline__ unsigned zpat32(unsigned z2) {   // two z bits of one half: bit 0 -> low 16 bits, bit 1 -> high 16
-  return (0u - (z2 & 1u)) & 0x0000FFFFu | (0u - ((z2 >> 1) & 1u)) & 0xFFFF0000u;
-}
-__device__ __forceinline__ unsigned long long mask_from_xy(unsigned xy, unsigned zm) {
-  return ((unsigned long long)(xy & zpat32(zm >> 2)) << 32) | (unsigned long long)(xy & zpat32(zm & 3u));
-}
-__device__ __forceinline__ unsigned long long mask_from_axes(unsigned xm, unsigned ym, unsigned zm) {
-  return mask_from_xy(xpat32(xm) & ypat32(ym), zm);
-}
 // voxels of block (bx,by,bz) that lie inside the 5x5x5 stencil around voxel (cvx,cvy,cvz)
-__device__ __forceinline__ unsigned axis_in_stencil(int b, int cv) {
-  const int lo = cv - 2 - 4 * b, hi = cv + 2 - 4 * b;   // local coordinate range of the stencil in this block
-  if (hi < 0 || lo > 3) return 0u;
-  const int l = lo < 0 ? 0 : lo, h = hi > 3 ? 3 : hi;
-  return ((1u << (h - l + 1)) - 1u) << l;
-}
 __device__ __forceinline__ unsigned long long block_stencil_mask(int bx, int by, int bz, int cvx, int cvy, int cvz) {
-  const unsigned xm = axis_in_stencil(bx, cvx), ym = axis_in_stencil(by, cvy), zm = axis_in_stencil(bz, cvz);
-  if (!(xm && ym && zm)) return 0ull;
+  // most callers' blocks lie outside the stencil: one unsigned compare per axis (stencil_axis_bits) settles them
+  const unsigned xm = stencil_axis_bits(bx, cvx);
+  if (!xm) return 0ull;
+  const unsigned ym = stencil_axis_bits(by, cvy), zm = stencil_axis_bits(bz, cvz);
+  if (!(ym && zm)) return 0ull;
   return mask_from_axes(xm, ym, zm);
 }
 
