@@ -35,6 +35,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  The reference's ikd-Tree (compiled unmodified into oracle/_ref for the CPU legs)
+# printf()s its own thread messages (ikd_Tree.cpp:176,314), also at process teardown: file descriptor 1 is therefore
+# pointed at stderr for the whole run and the JSON line is written to the saved real stdout.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 TINY = False  # --tiny: test-only shrink of the workload (NOT a bench configuration; used by tests/test_bench_dist.py)
 
 
@@ -194,7 +217,7 @@ def run_reference(args):
                             "sample": f"{args.steps} scans/step-loop after {args.warmup} warm-up; ikd-Tree = reference source "
                                       f"compiled unmodified (Build {build_s:.1f}s untimed); h_share_model/ESIKF = restated port"},
            "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_b200(args):
@@ -374,7 +397,7 @@ def run_b200(args):
             out["frontend"] = frontend
         if world_size == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(work, W)
-        print(json.dumps(out), flush=True)
+        emit(out)
     ses.close()
     tree.close()
     if world_size > 1:
@@ -490,6 +513,7 @@ def main():
     args = ap.parse_args()
     global TINY
     TINY = args.tiny
+    protect_stdout()
     if args.warmup < 3 and args.impl == "b200":
         log("note: timing rules ask for >= 3 warm-up steps")
     if args.impl == "reference":
