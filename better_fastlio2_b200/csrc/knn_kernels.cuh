@@ -27,9 +27,6 @@ constexpr int BLOCK_RINGS = 3;  // block shells searched by the exact kernel bef
 #ifndef FLB_KNN_MINB
 #define FLB_KNN_MINB 2
 #endif
-#ifndef FLB_KNN_SPLIT_F
-#define FLB_KNN_SPLIT_F 1.0f   // near/far boundary of the two-halves shell visit, in units of r block edges (tuning)
-#endif
 constexpr int KNN_THREADS = FLB_KNN_THREADS;
 constexpr int KNN_MIN_CTAS = FLB_KNN_MINB;
 
@@ -533,7 +530,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       // found, which usually prunes them all before a single probe.
       const bool need_split = go && gcount < K;
       const int nhalf = __any_sync(FULL, need_split) ? 2 : 1;    // warp-uniform
-      const float dsplit = need_split ? (float)(r * r) * bs4 * bs4 * (FLB_KNN_SPLIT_F * FLB_KNN_SPLIT_F) : CUDART_INF_F;
+      const float dsplit = need_split ? (float)(r * r) * bs4 * bs4 : CUDART_INF_F;
 #pragma unroll 1
       for (int half = 0; half < nhalf; ++half) {
       const float bound = gcount == K ? thr : CUDART_INF_F;
