@@ -339,7 +339,7 @@ def run_b200(args):
         npts_prof += len(work["scans"][k])
     prof = tree.profile_read(reset=True)
     tree.profile_enable(False)
-    frontend = frontend_rows(work, ses, fov, torch, local, W, rank) if not TINY else None
+    frontend = frontend_rows(work, ses, fov, torch, local, W, rank, cpu=(world_size == 1 and not args.no_cpu_baseline)) if not TINY else None
     ms_max, e2e_ms_max = dist_max([ms, e2e_s * 1e3], device=f"cuda:{local}")
     stats = tree.stats()
     if rank == 0:
@@ -404,7 +404,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def frontend_rows(work, ses, fov, torch, local, W, rank, S=20, leaf=0.5):
+def frontend_rows(work, ses, fov, torch, local, W, rank, S=20, leaf=0.5, cpu=True):
     """SURVEY.md §8f rows measured beside the headline (NOT part of `value`/`e2e`): the raw 120k-point scan goes
     host -> UndistortPcl backward pass -> pcl::VoxelGrid(leaf) -> update -> map_incremental ("Q-ds" query mode: the queries
     are the filtered scan, as laserMapping.cpp:2322 does), all through the C ABI from pinned host buffers; the CPU figure
@@ -467,7 +467,7 @@ def frontend_rows(work, ses, fov, torch, local, W, rank, S=20, leaf=0.5):
            "leaf": leaf, "raw_points_mean": float(np.mean([r.shape[0] for r in raw])), "down_points_mean": float(np.mean(nd)),
            "front_ms_per_scan": 1e3 * t_front, "scans_per_s_raw_to_posterior": 1.0 / t_all, "samples": S,
            "h2d_bytes_per_scan": int(48 * np.mean([r.shape[0] for r in raw]))}
-    if rank == 0:
+    if rank == 0 and cpu:   # part of the cpu_baseline leg (rank 0, N = 1 only): the oracle timed on one host core
         try:
             from oracle import pyoracle as po
             t0 = time.perf_counter()

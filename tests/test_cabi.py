@@ -79,3 +79,33 @@ int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(flb_map_config), s
     mine = [ctypes.sizeof(x) for x in (capi.MapConfig, capi.MapStats, capi.SessionConfig, capi.PassResult, capi.UpdateStats,
                                        capi.FovState, capi.ScanResult, capi.Profile)]
     assert sizes == mine, (sizes, mine)
+
+
+def test_frontend_entry_points_reject_bad_arguments(lib):
+    """Argument validation of the front-end rows runs before any device work: callable without a GPU."""
+    lib.flb_last_error.restype = ctypes.c_char_p
+    n = ctypes.c_int(-1)
+    vp = ctypes.c_void_p
+    lib.flb_voxel_grid_filter.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_int)]
+    assert lib.flb_voxel_grid_filter(None, None, 10, 48, 32, ctypes.c_float(0.5), None, 0, ctypes.byref(n)) != 0
+    assert b"null map" in lib.flb_last_error()
+    lib.flb_frontend_create.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
+    h = vp()
+    assert lib.flb_frontend_create(None, 1000, ctypes.byref(h)) != 0 and not h.value
+    lib.flb_frontend_upload.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    assert lib.flb_frontend_upload(None, None, 0, 48, 32, 36) != 0
+    assert b"null front end" in lib.flb_last_error()
+    lib.flb_map_reconstruct_keyframes.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_float, vp,
+                                                  ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    assert lib.flb_map_reconstruct_keyframes(None, None, None, 0, 48, 32, None, ctypes.c_float(0.4), None, 0, ctypes.byref(n)) != 0
+    lib.flb_frontend_destroy.argtypes = [vp]
+    lib.flb_frontend_destroy.restype = None
+    lib.flb_frontend_destroy(None)   # destroying a null handle is a no-op
+
+
+def test_header_cites_frontend_reference_interfaces():
+    src = open(HEADER).read()
+    for cite in ("IMU_Processing.hpp:243", ":334-386", "laserMapping.cpp:2322-2323", "laserMapping.cpp:1502-1540",
+                 "laserMapping.cpp:632-664", "common_lib.h:711-734", "msg/Pose6D.msg"):
+        assert cite in src, cite
