@@ -231,7 +231,8 @@ typedef struct flb_frontend flb_frontend;
 int flb_frontend_create(flb_session* s, int max_raw_points, flb_frontend** out);
 void flb_frontend_destroy(flb_frontend* f);
 /* meas.lidar (IMU_Processing.hpp:242 "pcl_out = *(meas.lidar)"): upload the raw scan. off_intensity / off_curvature are
- * byte offsets of those float fields inside a point, or -1 when absent (treated as 0). */
+ * byte offsets of those float fields inside a point, or -1 when absent (treated as 0).  The buffer holds n whole records
+ * (n * stride_bytes bytes are copied), as a std::vector<PointType> / pcl::PointCloud does. */
 int flb_frontend_upload(flb_frontend* f, const void* pts, int n, int stride_bytes, int off_intensity, int off_curvature);
 /* ImuProcess::UndistortPcl, the per-point part (IMU_Processing.hpp:243 sort by time, :334-386 backward compensation).
  * imu_poses = n_poses x 22 doubles = the IMUpose vector built by the forward propagation (:260-322, stays on the host
