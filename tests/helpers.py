@@ -62,3 +62,54 @@ def maps_match(a, b, tol=2e-6):
             return False, f"point {p} has no partner within tolerance (best {d[j]})"
         only_b = np.delete(only_b, j, 0)
     return True, f"{len(only_a)} coordinates differ by rounding"
+
+
+# ---------------------------------------------------------------------------------------------- size-independent properties
+def brute_knn_d2(points, q, k=5):
+    """k smallest squared distances from q to points in float32, (dx*dx + dy*dy) + dz*dz like calc_dist (ikd_Tree.cpp:1373)."""
+    p = np.asarray(points, np.float32)
+    q = np.asarray(q, np.float32)
+    d = ((p[:, 0] - q[0]) ** 2 + (p[:, 1] - q[1]) ** 2) + (p[:, 2] - q[2]) ** 2
+    k = min(k, len(d))
+    return np.sort(np.partition(d, k - 1)[:k])
+
+
+def map_properties(tree, queries, rng, n_brute=32):
+    """Properties every exact k-NN map must satisfy at ANY size (used on the CPU with the reference ikd-Tree at a small
+    size and on the GPU at BASELINE's full size): sorted distances, coordinates reproduce distances, agreement with a
+    brute-force scan of the map's own content, idempotence of the downsampled insert, box delete bookkeeping."""
+    queries = np.ascontiguousarray(queries, np.float32)
+    content = tree.flatten()
+    assert len(content) == tree.validnum() and len(content) >= 5
+    xyz, d2, cnt = tree.Nearest_Search(queries, 5)
+    assert (cnt == 5).all()
+    assert (np.diff(d2, axis=1) >= 0).all()                                     # ascending
+    dd = ((xyz[:, :, 0] - queries[:, None, 0]) ** 2 + (xyz[:, :, 1] - queries[:, None, 1]) ** 2) + \
+         (xyz[:, :, 2] - queries[:, None, 2]) ** 2
+    assert np.array_equal(dd.astype(np.float32), d2)                            # the returned points ARE at those distances
+    pick = rng.choice(len(queries), min(n_brute, len(queries)), replace=False)
+    for i in pick:
+        assert np.array_equal(brute_knn_d2(content, queries[i]), d2[i]), i      # exact: nothing nearer exists in the map
+    # downsampled insert twice = once (each touched voxel already holds its winner)
+    X = (queries[::3] + rng.normal(0, 0.03, (len(queries[::3]), 3))).astype(np.float32)
+    tree.Add_Points(X, True)
+    v1, c1 = tree.validnum(), sort_rows(tree.flatten())
+    tree.Add_Points(X, True)
+    assert tree.validnum() == v1
+    c2 = sort_rows(tree.flatten())
+    assert np.array_equal(c1, c2)
+    # box delete: count, emptiness of the half-open box, search still exact afterwards
+    ctr = np.median(queries, axis=0)
+    box = np.array([ctr[0] - 6, ctr[1] - 6, ctr[2] - 3, ctr[0] + 6, ctr[1] + 6, ctr[2] + 30], np.float32)
+    inside = ((c2 >= box[:3]) & (c2 < box[3:])).all(1)
+    nd = tree.Delete_Point_Boxes(box[None, :])
+    assert nd == int(inside.sum()) and nd > 0
+    after = tree.flatten()
+    assert len(after) == len(c2) - nd == tree.validnum()
+    assert not ((after >= box[:3]) & (after < box[3:])).all(1).any()
+    near = queries[((queries >= box[:3] - 1) & (queries < box[3:] + 1)).all(1)][:8]
+    if len(near):
+        _, d3, c3 = tree.Nearest_Search(near, 5)
+        for j in range(len(near)):
+            assert np.array_equal(brute_knn_d2(after, near[j]), d3[j][:c3[j]])
+    return dict(map_points=len(content), queries=len(queries), deleted=nd)

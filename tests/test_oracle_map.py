@@ -60,3 +60,19 @@ def test_small_and_empty_maps(oracle):
     port.Build(np.array([[1, 1, 1], [2, 2, 2]], np.float32))
     x, d, c = port.Nearest_Search(q, 5)
     assert (c == 2).all() and np.allclose(d[:, 0], 3.0) and np.isinf(d[:, 2:]).all()
+
+
+def test_size_independent_properties_on_reference_tree(oracle):
+    """The property harness of tests/helpers.map_properties (used at BASELINE's full size on the GPU) holds for the
+    reference's own ikd-Tree at a small size."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from tests.helpers import small_scene, map_properties
+    from better_fastlio2_b200 import synth
+    sc = small_scene(seed=21, map_half=30.0, half_extent=90.0)
+    t = oracle.RefIkdTree(ds=0.2)
+    t.Build(sc["map"][:20000])
+    t.Add_Points(sc["map"][20000:], True)
+    q = synth.body_to_world_np(sc["st_true"], sc["body"])[::5].astype(np.float32)
+    info = map_properties(t, q, np.random.default_rng(2))
+    assert info["deleted"] > 0
