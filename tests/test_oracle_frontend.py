@@ -166,3 +166,50 @@ def test_oracle_reproduces_frontend_golden(oracle):
         assert not ovf and np.array_equal(d, g[key]) and np.array_equal(dc, g[key + "_curv"])
     assert np.array_equal(oracle.transform_cloud_rpy(p4, g["pose6"]), g["transformed"])
     assert np.array_equal(oracle.body_to_world4(g["end"], g["down_stable"]), g["world"])
+
+
+# ---------------------------------------------------------------------------------------------- property-based checks
+from hypothesis import given, settings, strategies as st  # noqa: E402
+from hypothesis.extra import numpy as hnp  # noqa: E402
+
+_clouds = hnp.arrays(np.float32, st.tuples(st.integers(1, 200), st.just(4)),
+                     elements=st.floats(-50, 50, width=32, allow_nan=False, allow_infinity=False))
+
+
+@settings(max_examples=40, deadline=None)
+@given(p4=_clouds, leaf=st.sampled_from([0.1, 0.25, 0.5, 2.0]), seed=st.integers(0, 1000))
+def test_voxel_grid_invariants(p4, leaf, seed):
+    from oracle import pyoracle as po
+    out, _, ovf = po.voxel_grid(p4, leaf, order="stable")
+    assert not ovf and 1 <= len(out) <= len(p4)
+    # every centroid lies in the bounding box of the cloud; the leaves are a partition: a permutation of the input gives
+    # the same number of leaves and (up to float summation order) the same centroids in the same leaf order
+    tol = 2e-3   # float32 accumulation of up to 200 coordinates of magnitude 50 (PCL sums in float too)
+    assert (out[:, :3] >= p4[:, :3].min(0) - tol).all() and (out[:, :3] <= p4[:, :3].max(0) + tol).all()
+    perm = np.random.default_rng(seed).permutation(len(p4))
+    out2, _, _ = po.voxel_grid(p4[perm], leaf, order="stable")
+    assert len(out2) == len(out)
+    assert np.abs(out2 - out).max() <= tol
+    # PCL's own in-leaf order (std::sort) only changes rounding
+    out3, _, _ = po.voxel_grid(p4, leaf, order="pcl")
+    assert len(out3) == len(out) and np.abs(out3 - out).max() <= tol
+    # total mass: leaf counts are implied by sum(points) = sum(count * centroid); check with counts from numpy
+    ref, cnt = _np_voxel_grid(p4, leaf)
+    assert len(ref) == len(out) and int(cnt.sum()) == len(p4)
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(1, 300), seed=st.integers(0, 10000))
+def test_undistort_at_rest_is_identity_and_sorted(n, seed):
+    """A sensor at rest (zero velocity / rates, poses equal to the end state) must leave every point where it is; the
+    output is in time order whatever the input order."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-30, 30, (n, 3)).astype(np.float32)
+    cur = rng.uniform(0, 100, n).astype(np.float32)
+    st0 = synth.make_state(pos=(1.5, -2.0, 0.7))
+    R = synth.quat_to_mat(st0[3:7]).reshape(-1)
+    poses = np.array([np.concatenate([[0.02 * k], np.zeros(3), np.zeros(3), np.zeros(3), st0[0:3], R]) for k in range(6)])
+    out, perm = po.undistort(xyz, cur, poses, st0)
+    assert (np.diff(cur[perm]) >= 0).all()
+    assert np.abs(out - xyz[perm]).max() <= 4e-6 * 30      # float rounding of the (identity) double transform chain
