@@ -18,7 +18,7 @@ FLB_HD unsigned ypat32(unsigned ym) {                              // nibble y o
   return (sp * 0xFu) * 0x00010001u;
 }
 FLB_HD unsigned zpat32(unsigned z2) {   // two z bits of one half: bit 0 -> low 16 bits, bit 1 -> high 16
-  return (0u - (z2 & 1u)) & 0x0000FFFFu | (0u - ((z2 >> 1) & 1u)) & 0xFFFF0000u;
+  return ((0u - (z2 & 1u)) & 0x0000FFFFu) | ((0u - ((z2 >> 1) & 1u)) & 0xFFFF0000u);
 }
 FLB_HD unsigned long long mask_from_xy(unsigned xy, unsigned zm) {
   return ((unsigned long long)(xy & zpat32(zm >> 2)) << 32) | (unsigned long long)(xy & zpat32(zm & 3u));
