@@ -488,7 +488,7 @@ def cpu_baseline(work, W):
     """Bounded sample of the same workload on the host cores with the reference's own thread policy (MP_PROC_NUM = 3,
     CMakeLists.txt:11-24)."""
     threads = 3
-    S = 6
+    S = max(1, min(24, len(work["scans"]) - 1))   # ~10 s of CPU work at ~0.4 s per scan (bounded sample)
     mp, step, build_s = cpu_step_runner(work, threads)
     step(0)
     t0 = time.perf_counter()
