@@ -98,6 +98,9 @@ struct flb_map {
   int* worklist = nullptr;       // unresolved-query list of the stencil k-NN kernel
   int work_cap = 0;
   bool scratch_clean = false;    // the downsample scratch hash was already cleared off the critical path (scan graph)
+  int gen = 0;                   // bumped whenever a buffer or parameter baked into a captured scan graph changes (scratch hash,
+                                 // work list, voxel size): sessions re-capture their graphs on a mismatch
+  bool warned_range = false;
   int knn_group = 32;            // lanes per query of the exact k-NN kernel: a whole warp (measured 2557 vs 2251 scans/s for 8,
                                  // profiles/r1d_*); FLB_KNN_GROUP=8 selects four queries per warp (tuning only)
 };
@@ -127,8 +130,8 @@ static int dev_alloc(flb_map* m, void** p, size_t bytes) {
 static int map_reset_storage(flb_map* m) {
   MapDev& d = m->d;
   cudaStream_t st = m->stream;
-  CU(cudaMemsetAsync(d.hent, 0xFF, sizeof(HEntry) * m->hash_cap, st));
-  CU(cudaMemsetAsync(d.bmask, 0, sizeof(uint64_t) * d.block_cap, st));
+  k_hent_clear<<<m->sm_count * 8, 256, 0, st>>>(d.hent, m->hash_cap);
+  CU(cudaGetLastError());
   CU(cudaMemsetAsync(d.slots, 0xFF, sizeof(float4) * 64 * (size_t)d.block_cap, st));
   CU(cudaMemsetAsync(d.bkey, 0xFF, sizeof(uint64_t) * d.block_cap, st));
   CU(cudaMemsetAsync(d.brel, 0, sizeof(uint64_t) * d.block_cap, st));
@@ -145,10 +148,27 @@ static int map_reset_storage(flb_map* m) {
   return 0;
 }
 
+// A NaN / out-of-range point is skipped by the insert kernels (the reference keeps running in that situation too): the
+// flag is reported once and cleared, so that one bad point does not fail every later call.  Capacity errors stay sticky.
+static int absorb_range_flag(flb_map* m) {
+  int e = m->h_counters[CNT_ERROR];
+  if (!(e & ERR_RANGE)) return e;
+  if (!m->warned_range) {
+    fprintf(stderr, "[fastlio_b200] warning: point(s) outside the representable range / NaN were skipped by the map insert\n");
+    m->warned_range = true;
+  }
+  e &= ~ERR_RANGE;
+  m->h_counters[CNT_ERROR] = e;
+  // the stream is drained here (callers synchronised): a plain store of the remaining (sticky) bits is race free
+  if (cudaMemcpyAsync(m->d.counters + CNT_ERROR, m->h_counters + CNT_ERROR, sizeof(int), cudaMemcpyHostToDevice, m->stream) == cudaSuccess)
+    cudaStreamSynchronize(m->stream);
+  return e;
+}
+
 static int fetch_counters(flb_map* m) {
   CU(cudaMemcpyAsync(m->h_counters, m->d.counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
-  const int e = m->h_counters[CNT_ERROR];
+  const int e = absorb_range_flag(m);
   if (e) {
     return set_err("device map error flags 0x%x:%s%s%s%s%s", e, (e & ERR_BLOCKS_FULL) ? " block pool exhausted (raise max_blocks)" : "",
                    (e & ERR_OVF_FULL) ? " overflow pool exhausted (raise max_points)" : "", (e & ERR_HASH_FULL) ? " block hash full" : "",
@@ -185,7 +205,7 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   d.chash_mask = m->chash_cap - 1;
   int rc = 0;
   rc |= dev_alloc(m, (void**)&d.hent, sizeof(HEntry) * m->hash_cap);
-  rc |= dev_alloc(m, (void**)&d.bmask, sizeof(uint64_t) * d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.bslot, sizeof(uint32_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.slots, sizeof(float4) * 64 * (size_t)d.block_cap);
   rc |= dev_alloc(m, (void**)&d.ovf, sizeof(float4) * (size_t)d.ovf_cap);
   rc |= dev_alloc(m, (void**)&d.bkey, sizeof(uint64_t) * d.block_cap);
@@ -221,7 +241,7 @@ static void map_release(flb_map* m) {
   Q(cudaSetDevice(m->cfg.device));
   if (m->stream) Q(cudaStreamSynchronize(m->stream));
   MapDev& d = m->d;
-  void* ptrs[] = {d.clist, d.hent, d.bmask, d.slots, d.ovf, d.bkey, d.brel, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
+  void* ptrs[] = {d.clist, d.hent, d.bslot, d.slots, d.ovf, d.bkey, d.brel, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
                   m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
   for (void* p : ptrs) if (p) Q(cudaFree(p));
   if (m->h_counters) Q(cudaFreeHost(m->h_counters));
@@ -239,6 +259,7 @@ extern "C" int flb_map_set_downsample_param(flb_map* m, float v) {
   if (m->h_counters[CNT_VALID] != 0) return set_err("set_downsample_param: map not empty (voxel hashing depends on the voxel size)");
   m->d.ds = v;
   m->cfg.voxel_size = v;
+  m->gen++;
   return 0;
 }
 extern "C" int flb_map_has_root(const flb_map* m) { return m && m->has_root ? 1 : 0; }
@@ -285,6 +306,7 @@ static int ensure_scratch(flb_map* m, int n) {
     CU(cudaMalloc((void**)&m->skeys, sizeof(uint64_t) * need));
     CU(cudaMalloc((void**)&m->sbest, sizeof(unsigned long long) * need));
     m->scratch_cap = need;
+    m->gen++;
   }
   return 0;
 }
@@ -416,7 +438,9 @@ static int maybe_rehash(flb_map* m) {
   if (m->h_counters[CNT_KEYS_TOMB] <= (int)(m->hash_cap / 8)) return 0;
   const int nblk = blocks_bumped(m);
   cudaStream_t st = m->stream;
-  CU(cudaMemsetAsync(m->d.hent, 0xFF, sizeof(HEntry) * m->hash_cap, st));
+  k_rehash_save<<<grid_for(nblk, 256, m->sm_count * 8), 256, 0, st>>>(m->d, nblk);
+  k_hent_clear<<<m->sm_count * 8, 256, 0, st>>>(m->d.hent, m->hash_cap);
+  m->launches += 2;
   CU(cudaMemsetAsync(m->d.ckeys, 0xFF, sizeof(uint64_t) * m->chash_cap, st));
   CU(cudaMemsetAsync(m->d.cbits, 0, sizeof(uint64_t) * 8 * (size_t)m->chash_cap, st));
   int init[8] = {0, 0, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
@@ -441,6 +465,7 @@ static int launch_knn(flb_map* m, KnnArgs a) {
     const int cap = std::max(a.n, 1 << 17);
     CU(cudaMalloc((void**)&m->worklist, sizeof(int) * (size_t)cap));
     m->work_cap = cap;
+    m->gen++;
   }
   a.worklist = m->worklist;
   if (a.stride <= 0) a.stride = a.n;
@@ -633,7 +658,7 @@ struct flb_session {
   flb_map* map = nullptr;
   flb_session_config cfg{};
   int cap = 0, n = 0;
-  float4 *body = nullptr, *world = nullptr, *nbr = nullptr, *normvec = nullptr;
+  float4 *body = nullptr, *world = nullptr, *nbr = nullptr, *normvec = nullptr, *plane = nullptr;
   unsigned char *cnt = nullptr, *sel = nullptr, *cls = nullptr;
   double *partial = nullptr, *dout = nullptr;
   int* offs = nullptr;
@@ -663,6 +688,7 @@ struct flb_session {
   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [0] update only, [1] update + map_incremental
   cudaGraphExec_t graph_alt[2] = {nullptr, nullptr};  // the same sequences captured for the other body buffer
   int graph_kernels[2] = {0, 0}, graph_kernels_alt[2] = {0, 0};
+  int graph_gen = -1;            // flb_map::gen the graphs were captured at
   bool use_graph = true;
   // double-buffered scan upload (flb_scan_prefetch)
   float4* body_alt = nullptr;
@@ -707,6 +733,7 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   A((void**)&s->world, sizeof(float4) * N);
   A((void**)&s->nbr, sizeof(float4) * N * 5);
   A((void**)&s->normvec, sizeof(float4) * N);
+  A((void**)&s->plane, sizeof(float4) * N);
   A((void**)&s->cnt, N);
   A((void**)&s->sel, N);
   A((void**)&s->cls, N);
@@ -763,7 +790,7 @@ extern "C" void flb_session_destroy(flb_session* s) {
     if (s->graph[i]) Q(cudaGraphExecDestroy(s->graph[i]));
     if (s->graph_alt[i]) Q(cudaGraphExecDestroy(s->graph_alt[i]));
   }
-  void* ptrs[] = {s->body, s->body_alt, s->world, s->nbr, s->normvec, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
+  void* ptrs[] = {s->body, s->body_alt, s->world, s->nbr, s->normvec, s->plane, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
                   s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->raw_alt, s->ctl, s->d_x0P0, s->d_scr};
   for (void* p : ptrs) if (p) Q(cudaFree(p));
   if (s->h_out) Q(cudaFreeHost(s->h_out));
@@ -888,7 +915,7 @@ static PoseDev pose_from(const double* st) {
 static MeasArgs meas_args(flb_session* s, const PoseDev& pose, int search) {
   MeasArgs a;
   a.pose = pose; a.body = s->body; a.world = s->world; a.nbr = s->nbr; a.cnt = s->cnt; a.sel = s->sel;
-  a.normvec = s->normvec; a.partial = s->partial; a.n = s->n; a.search = search;
+  a.normvec = s->normvec; a.plane = s->plane; a.partial = s->partial; a.n = s->n; a.search = search;
   a.ctl = nullptr; a.world_out = s->world; a.stride = s->cap;
   return a;
 }
@@ -1123,6 +1150,13 @@ static int launch_scan_device(flb_session* s, const double* state26, const doubl
   s->h_x0P0[26 + NDOF * NDOF + 1] = (double)flg_EKF_inited;
   const int gi = with_insert ? 1 : 0;
   if (!s->use_graph || m->prof_on) return enqueue_scan_device(s, with_insert);
+  if (s->graph_gen != m->gen) {
+    // a buffer baked into the captured sequences was reallocated (or the voxel size changed) since: capture again
+    for (int i = 0; i < 2; ++i) {
+      if (s->graph[i]) { Q(cudaGraphExecDestroy(s->graph[i])); s->graph[i] = nullptr; }
+      if (s->graph_alt[i]) { Q(cudaGraphExecDestroy(s->graph_alt[i])); s->graph_alt[i] = nullptr; }
+    }
+  }
   if (!s->graph[gi]) {
     // everything the captured sequence may allocate lazily must exist before capture
     if (ensure_scratch(m, s->cap)) return 1;
@@ -1131,6 +1165,7 @@ static int launch_scan_device(flb_session* s, const double* state26, const doubl
       m->worklist = nullptr; m->work_cap = 0;
       CU(cudaMalloc((void**)&m->worklist, sizeof(int) * (size_t)std::max(s->cap, 1 << 17)));
       m->work_cap = std::max(s->cap, 1 << 17);
+      m->gen++;
     }
     CU(cudaStreamSynchronize(m->stream));
     const int l0 = m->launches;
@@ -1156,13 +1191,14 @@ static int launch_scan_device(flb_session* s, const double* state26, const doubl
     }
     s->graph_kernels[gi] = m->launches - l0;
     m->launches = l0;
+    s->graph_gen = m->gen;
   }
   CU(cudaGraphLaunch(s->graph[gi], m->stream));
   m->launches += s->graph_kernels[gi];
   return 0;
 }
 static int finish_counters(flb_map* m) {  // after the stream drained: interpret the counters copied by the sequence
-  const int e = m->h_counters[CNT_ERROR];
+  const int e = absorb_range_flag(m);
   if (e) return set_err("device map error flags 0x%x (capacity exceeded or point out of range; see flb_map_get_stats)", e);
   return 0;
 }
@@ -1326,6 +1362,7 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
                                    const double* P, int flg_EKF_inited) {
   if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
   flb_map* m = s->map;
+  if (s->step_pending) return set_err("flb_scan_step_begin: the previous step has not been collected (call flb_scan_step_finish first)");
   CU(cudaSetDevice(m->cfg.device));
   s->step_l0 = m->launches;
   s->step_deleted = 0;

@@ -277,10 +277,7 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
       }
       int blk = -1;
       unsigned long long mask = 0ull;
-      if (go) {
-        blk = find_block(m, pack_key(bx, by, bz));
-        if (blk >= 0) mask = __ldg(&m.bmask[blk]);
-      }
+      if (go) blk = find_block_mask(m, pack_key(bx, by, bz), mask);
       const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
       if (todo) coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, false, fminf(lim, bound), t);
     }
@@ -538,6 +535,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       for (int base = 0; base < nb; base += 4 * G) {
         int off[4], blk[4];   // off: packed block offsets (dx+8) | (dy+8) << 4 | (dz+8) << 8, -1 = no probe
         uint4 ent[4];
+        unsigned long long mask[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int idx = base + G * u + gl;
@@ -552,7 +550,9 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
               const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);
               if (!(md > bound || md > lim) && (half == 0 ? md <= dsplit : md > dsplit)) {
                 off[u] = (dx + 8) | ((dy + 8) << 4) | ((dz + 8) << 8);
-                ent[u] = __ldg(reinterpret_cast<const uint4*>(&m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask]));
+                const HEntry* he = &m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask];
+                ent[u] = __ldg(reinterpret_cast<const uint4*>(he));
+                mask[u] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));   // same 32-B sector
               }
             }
           }
@@ -563,12 +563,11 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
           if (off[u] >= 0) {
             const uint64_t key = pack_key(qbx + (off[u] & 15) - 8, qby + ((off[u] >> 4) & 15) - 8, qbz + (off[u] >> 8) - 8);
             const uint64_t k0 = ((uint64_t)ent[u].y << 32) | ent[u].x;
-            blk[u] = (k0 == key) ? (int)ent[u].z : (k0 == KEY_EMPTY ? -1 : find_block(m, key));
-          }
+            if (k0 == key) blk[u] = (int)ent[u].z;
+            else if (k0 == KEY_EMPTY) { blk[u] = -1; mask[u] = 0ull; }
+            else blk[u] = find_block_mask(m, key, mask[u]);   // collision: sequential probe
+          } else mask[u] = 0ull;
         }
-        unsigned long long mask[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mask[u] = blk[u] >= 0 ? __ldg(&m.bmask[blk[u]]) : 0ull;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const unsigned bal = __ballot_sync(FULL, blk[u] >= 0 && mask[u] != 0ull);
@@ -831,22 +830,25 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     }
     // ---- the 8 hash probes are INDEPENDENT loads: issue them back to back (memory-level parallelism), then resolve;
     // only a collision (first slot holds another key) falls back to the sequential probe loop
-    uint64_t keys8[8];
+    // (one 32-byte sector per entry: key + block index in the first half, the occupancy word in the second — the block
+    // index and the occupied voxels arrive in ONE round trip, the point loads are the second and last dependent level)
     uint4 ent[8];
+    unsigned long long occ[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      keys8[b] = pack_key(bbx + (b & 1), bby + ((b >> 1) & 1), bbz + (b >> 2));
-      ent[b] = __ldg(reinterpret_cast<const uint4*>(&m.hent[hash_key(keys8[b]) & m.hash_mask]));
+      const HEntry* he = &m.hent[hash_key(pack_key(bbx + (b & 1), bby + ((b >> 1) & 1), bbz + (b >> 2))) & m.hash_mask];
+      ent[b] = __ldg(reinterpret_cast<const uint4*>(he));
+      occ[b] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));
     }
     int blk8[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
+      const uint64_t key = pack_key(bbx + (b & 1), bby + ((b >> 1) & 1), bbz + (b >> 2));
       const uint64_t k0 = ((uint64_t)ent[b].y << 32) | ent[b].x;
-      blk8[b] = (k0 == keys8[b]) ? (int)ent[b].z : (k0 == KEY_EMPTY ? -1 : find_block(m, keys8[b]));
+      if (k0 == key) blk8[b] = (int)ent[b].z;
+      else if (k0 == KEY_EMPTY) { blk8[b] = -1; occ[b] = 0ull; }
+      else blk8[b] = find_block_mask(m, key, occ[b]);   // collision: sequential probe
     }
-    unsigned long long occ[8];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) occ[b] = blk8[b] >= 0 ? __ldg(&m.bmask[blk8[b]]) : 0ull;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       sm.blk[b][tid] = blk8[b];

@@ -100,6 +100,7 @@ __device__ __forceinline__ void touch_block(const MapDev& m, uint64_t key, int b
         m.hent[s].val = (uint32_t)blk;  // -1 on exhaustion (sticky error already raised)
         if (blk >= 0) {
           m.bkey[blk] = key;
+          m.bslot[blk] = s;               // (entry mask is 0: cleared at reset / release)
           coarse_set(m, bx, by, bz);
         }
         atomicAdd(&m.counters[CNT_KEYS_USED], 1);
@@ -141,12 +142,13 @@ __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const 
     const float4 p = pts[i];
     if (!coord_ok(p.x, p.y, p.z, m.ds)) continue;
     const int vx = voxel_of(p.x, m.ds), vy = voxel_of(p.y, m.ds), vz = voxel_of(p.z, m.ds);
-    const int blk = find_block(m, pack_key(vx >> 2, vy >> 2, vz >> 2));
+    const int hs = find_slot(m, pack_key(vx >> 2, vy >> 2, vz >> 2));
+    const int blk = hs >= 0 ? (int)m.hent[hs].val : -1;
     if (blk < 0) continue;  // capacity error already flagged
     const int s = (((vz & 3) << 2) + (vy & 3)) * 4 + (vx & 3);
     const unsigned long long bit = 1ull << s;
     const size_t idx = (size_t)blk * 64 + s;
-    const unsigned long long old = atomicOr((unsigned long long*)&m.bmask[blk], bit);
+    const unsigned long long old = atomicOr((unsigned long long*)&m.hent[hs].mask, bit);
     if (!(old & bit)) {
       // owner of the head slot: write xyz only — w (= -1 by invariant) may concurrently receive a chain push
       float* f = reinterpret_cast<float*>(&m.slots[idx]);
@@ -297,16 +299,17 @@ __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsig
       s = (s + 1) & smask;
     }
     if (!mine) continue;
-    const int blk = find_block(m, pack_key(vx >> 2, vy >> 2, vz >> 2));
+    const int hs = find_slot(m, pack_key(vx >> 2, vy >> 2, vz >> 2));
+    const int blk = hs >= 0 ? (int)m.hent[hs].val : -1;
     if (blk < 0) continue;
     const int sl = (((vz & 3) << 2) + (vy & 3)) * 4 + (vx & 3);
     const unsigned long long bit = 1ull << sl;
     const size_t idx = (size_t)blk * 64 + sl;
-    const unsigned long long mask = m.bmask[blk];
+    const unsigned long long mask = *reinterpret_cast<volatile unsigned long long*>(&m.hent[hs].mask);
     if (!(mask & bit)) {
       float* f = reinterpret_cast<float*>(&m.slots[idx]);
       f[0] = p.x; f[1] = p.y; f[2] = p.z;  // w stays -1
-      atomicOr((unsigned long long*)&m.bmask[blk], bit);
+      atomicOr((unsigned long long*)&m.hent[hs].mask, bit);
       atomicAdd(&m.counters[CNT_VALID], 1);
       atomicAdd(&m.counters[CNT_SCRATCH0], 1);
       continue;
@@ -353,7 +356,7 @@ __device__ __forceinline__ void release_block(const MapDev& m, int blk, uint64_t
   uint32_t s = hash_key(key) & m.hash_mask;
   for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
     uint64_t k = *((volatile uint64_t*)&m.hent[s].key);
-    if (k == key) { m.hent[s].key = KEY_TOMB; break; }
+    if (k == key) { m.hent[s].mask = 0ull; m.hent[s].key = KEY_TOMB; break; }
     if (k == KEY_EMPTY) break;
     s = (s + 1) & m.hash_mask;
   }
@@ -393,7 +396,7 @@ __global__ void k_delete(MapDev m, const float* __restrict__ params, int np, int
       }
     }
     if (!touch) continue;  // warp-uniform
-    const unsigned long long mask = m.bmask[b];
+    const unsigned long long mask = *block_mask_ptr(m, b);
     unsigned long long clear = 0ull;
     int ndel = 0;
     for (int h = 0; h < 2; ++h) {
@@ -436,7 +439,7 @@ __global__ void k_delete(MapDev m, const float* __restrict__ params, int np, int
       atomicAdd(&m.counters[CNT_SCRATCH0], ndel);
       atomicSub(&m.counters[CNT_VALID], ndel);
       const unsigned long long nm = mask & ~clear;
-      m.bmask[b] = nm;
+      *block_mask_ptr(m, b) = nm;
       if (nm == 0ull) release_block(m, b, key);
     }
   }
@@ -451,7 +454,7 @@ __global__ void k_collect(MapDev m, int nblk, int mode, const float* __restrict_
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nblk; b += warps_per_grid) {
     if (m.bkey[b] == KEY_EMPTY) continue;
-    const unsigned long long mask = m.bmask[b];
+    const unsigned long long mask = *block_mask_ptr(m, b);
     auto pass = [&](const float4 q) -> bool {
       if (mode == 0) return true;
       if (mode == 1) return in_box(q, params);
@@ -505,7 +508,7 @@ __global__ void k_range(MapDev m, int nblk, int* box6ord) {
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nblk; b += warps_per_grid) {
     if (m.bkey[b] == KEY_EMPTY) continue;
-    const unsigned long long mask = m.bmask[b];
+    const unsigned long long mask = *block_mask_ptr(m, b);
     for (int h = 0; h < 2; ++h) {
       const int s = lane + 32 * h;
       if (!((mask >> s) & 1ull)) continue;
@@ -521,7 +524,20 @@ __global__ void k_range(MapDev m, int nblk, int* box6ord) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------- rehash (drop tombstones)
+// ---------------------------------------------------------------------------------------------- hash table (re)initialisation
+__global__ void k_hent_clear(HEntry* hent, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    HEntry e;
+    e.key = KEY_EMPTY; e.val = 0xFFFFFFFFu; e.pad = 0u; e.mask = 0ull; e.pad2 = 0ull;
+    hent[i] = e;
+  }
+}
+// rehash (drop tombstones), step 1: park every live block's occupancy word in the per-block scratch brel
+__global__ void k_rehash_save(MapDev m, int nblk) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x)
+    if (m.bkey[b] != KEY_EMPTY) m.brel[b] = m.hent[m.bslot[b]].mask;
+}
+// step 2 (after k_hent_clear): re-insert the keys with their occupancy words; brel goes back to all-zero
 __global__ void k_rehash_insert(MapDev m, int nblk) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x) {
     const uint64_t key = m.bkey[b];
@@ -529,7 +545,7 @@ __global__ void k_rehash_insert(MapDev m, int nblk) {
     uint32_t s = hash_key(key) & m.hash_mask;
     for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
       uint64_t old = atomicCAS((unsigned long long*)&m.hent[s].key, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-      if (old == KEY_EMPTY) { m.hent[s].val = (uint32_t)b; break; }
+      if (old == KEY_EMPTY) { m.hent[s].val = (uint32_t)b; m.hent[s].mask = m.brel[b]; m.bslot[b] = s; m.brel[b] = 0ull; break; }
       s = (s + 1) & m.hash_mask;
     }
     int bx, by, bz;

@@ -173,6 +173,8 @@ struct MeasArgs {
   const unsigned char* cnt;   // [n]
   unsigned char* sel;         // [n] point_selected_surf (in/out)
   float4* normvec;            // [n] (nx,ny,nz,pd2)
+  float4* plane;              // [n] pabcd of the last search pass (valid wherever sel survived it): the plane is a function of
+                              // the 5 cached neighbours only, so the passes that re-use Nearest_Points re-use it bit for bit
   double* partial;            // [gridDim.x][NACC]
   int n;
   int search;                 // ekfom_data.converge
@@ -223,17 +225,25 @@ __device__ __forceinline__ bool select_point(const MeasArgs& a, int i, int searc
     const float d4 = a.nbr[(size_t)4 * a.stride + i].w;
     sel = (c < 5) ? false : (d4 > 5.f ? false : true);        // :1911
   } else {
-    sel = a.sel[i] != 0;
+    sel = a.sel[i] != 0 && a.cnt[i] >= 5;   // (cnt is cleared per scan: a cached pass without a preceding search selects nothing)
   }
   if (!sel) return false;
-  float P[5][3];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const float4 q = a.nbr[(size_t)j * a.stride + i];
-    P[j][0] = q.x; P[j][1] = q.y; P[j][2] = q.z;
-  }
   float pa, pb_, pc, pd;
-  if (!esti_plane_dev(P, 0.1f, pa, pb_, pc, pd)) return false;
+  if (search) {
+    float P[5][3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float4 q = a.nbr[(size_t)j * a.stride + i];
+      P[j][0] = q.x; P[j][1] = q.y; P[j][2] = q.z;
+    }
+    if (!esti_plane_dev(P, 0.1f, pa, pb_, pc, pd)) return false;
+    a.plane[i] = make_float4(pa, pb_, pc, pd);
+  } else {
+    // same Nearest_Points as the last search pass => esti_plane (laserMapping.cpp:1922) returns the same plane: sel[i]
+    // can only still be set if that fit was accepted, so the cached coefficients are exactly what it would recompute
+    const float4 pl = a.plane[i];
+    pa = pl.x; pb_ = pl.y; pc = pl.z; pd = pl.w;
+  }
   const float4 pb = a.body[i];
   const float pd2 = pa * pw.x + pb_ * pw.y + pc * pw.z + pd;  // :1925 (float, left to right)
   const double bn = sqrt((double)pb.x * (double)pb.x + (double)pb.y * (double)pb.y + (double)pb.z * (double)pb.z);

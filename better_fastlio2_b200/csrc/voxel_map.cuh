@@ -7,8 +7,10 @@
 //   coarse c = b >> 3   (8x8x8 blocks; 512-bit block-occupancy bitmap) — only used to bound far searches.
 //
 // Storage in HBM
-//   hent[C]           open-addressing hash  block key -> block index   (C = 2^k >= 2*B, one 16-B entry per slot)
-//   bmask[B]          64-bit voxel occupancy of a block
+//   hent[C]           open-addressing hash  block key -> {block index, 64-bit voxel occupancy of the block}
+//                     (C = 2^k >= 2*B, one 32-B entry = one DRAM sector per slot: a k-NN probe learns the block index AND
+//                     which of its voxels hold points from ONE memory round trip; the occupancy word lives only here)
+//   bslot[B]          hash slot of each allocated block (for the kernels that iterate blocks densely)
 //   slots[B*64]       float4 head point of each voxel: x,y,z and w = int index of an overflow node (-1: none).
 //                     INVARIANT: w == -1 whenever the voxel has no overflow chain (also while the voxel is empty).
 //   ovf[O]            float4 overflow nodes (x,y,z, w = next) for the rare voxels holding > 1 point
@@ -49,16 +51,18 @@ enum Counter : int {
 };
 enum DevError : int { ERR_BLOCKS_FULL = 1, ERR_OVF_FULL = 2, ERR_HASH_FULL = 4, ERR_COARSE_FULL = 8, ERR_RANGE = 16 };
 
-// one hash entry: key and block index side by side so that a lookup is ONE 16-byte load
-struct __align__(16) HEntry {
+// one hash entry = one 32-byte sector: key, block index and the block's voxel-occupancy word side by side
+struct __align__(32) HEntry {
   uint64_t key;
   uint32_t val;
   uint32_t pad;
+  uint64_t mask;   // bit s set <=> voxel slot s of the block holds >= 1 point (0 for empty / tombstoned entries)
+  uint64_t pad2;
 };
 
 struct MapDev {
   HEntry* hent;
-  uint64_t* bmask;
+  uint32_t* bslot;
   float4* slots;
   float4* ovf;
   uint64_t* bkey;
@@ -136,6 +140,37 @@ __device__ __forceinline__ int find_block(const MapDev& m, uint64_t key) {
     s = (s + 1) & m.hash_mask;
   }
   return -1;
+}
+// Same, returning the hash slot (or -1): the entry holds the block index (val) and the occupancy word (mask).
+__device__ __forceinline__ int find_slot(const MapDev& m, uint64_t key) {
+  uint32_t s = hash_key(key) & m.hash_mask;
+  for (int probe = 0; probe <= (int)m.hash_mask; ++probe) {
+    const uint64_t k = *reinterpret_cast<const volatile uint64_t*>(&m.hent[s].key);
+    if (k == key) return (int)s;
+    if (k == KEY_EMPTY) return -1;
+    s = (s + 1) & m.hash_mask;
+  }
+  return -1;
+}
+// Read-only probe for the k-NN kernels: block index (or -1) and its occupancy word from the entry's sector.
+__device__ __forceinline__ int find_block_mask(const MapDev& m, uint64_t key, unsigned long long& mask) {
+  uint32_t s = hash_key(key) & m.hash_mask;
+  for (int probe = 0; probe <= (int)m.hash_mask; ++probe) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(&m.hent[s]));
+    const uint64_t k = ((uint64_t)e.y << 32) | e.x;
+    if (k == key) {
+      mask = __ldg(reinterpret_cast<const unsigned long long*>(&m.hent[s].mask));
+      return (int)e.z;
+    }
+    if (k == KEY_EMPTY) break;
+    s = (s + 1) & m.hash_mask;
+  }
+  mask = 0ull;
+  return -1;
+}
+// occupancy word of an allocated block (block-iterating kernels)
+__device__ __forceinline__ unsigned long long* block_mask_ptr(const MapDev& m, int blk) {
+  return reinterpret_cast<unsigned long long*>(&m.hent[m.bslot[blk]].mask);
 }
 // Coarse-cell lookup. Returns slot index in ckeys/cbits or -1.
 __device__ __forceinline__ int find_coarse(const MapDev& m, uint64_t key) {

@@ -29,6 +29,17 @@ class World:
         self.hi = np.asarray(self.hi, np.float64).reshape(-1, 2)
         return self
 
+    def shifted(self, d):
+        """The same world translated by d = (dx, dy, dz) (call after finalize)."""
+        d = np.asarray(d, np.float64)
+        w = World()
+        w.axis = self.axis.copy()
+        w.coord = self.coord + d[self.axis]
+        uv = np.array([_OTHER[int(a)] for a in self.axis], np.int64).reshape(-1, 2)
+        w.lo = self.lo + d[uv]
+        w.hi = self.hi + d[uv]
+        return w
+
     def add_box(self, lo, hi):
         """Four walls and a roof of a building lo=(x0,y0,z0), hi=(x1,y1,z1)."""
         (x0, y0, z0), (x1, y1, z1) = lo, hi
