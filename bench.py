@@ -69,6 +69,7 @@ def emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
+NCU_SHORT = False  # --ncu-short: the same workload, cut to a few steps (every kernel is replayed by the profiler)
 TINY = False  # --tiny: test-only shrink of the workload (NOT a bench configuration; used by tests/test_bench_dist.py)
 
 
@@ -77,7 +78,7 @@ def n_scans_default():
 
 
 def parity_frames_default():
-    return 3 if TINY else PARITY_FRAMES
+    return 3 if (TINY or NCU_SHORT) else PARITY_FRAMES
 
 
 SENSOR_HEIGHT = 1.8  # the world origin is the first sensor pose (as in a FAST-LIO run): the ground plane is at z = -1.8 m
@@ -347,7 +348,7 @@ def run_b200(args):
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, K = args.warmup, args.steps
-    PROF = 10 if not TINY else 2  # profiled steps (per-kernel CUDA-event timing) after the timed regions
+    PROF = 10 if not (TINY or NCU_SHORT) else 2  # profiled steps (per-kernel CUDA-event timing) after the timed regions
     NS, F = n_scans_default(), parity_frames_default()
     t_gen = time.perf_counter()
     work = make_workload(SEED + rank, NS)  # cfg5: independent sessions, seeds 20..27
@@ -388,6 +389,8 @@ def run_b200(args):
 
     def cycle_blocks(w):
         starts = list(range(w, NS - K + 1, K)) or [w]
+        if NCU_SHORT:
+            starts = starts[:1]
         return [[(s0 + j) % NS for j in range(K)] for s0 in starts]
 
     def begin_cycle(first):
@@ -467,7 +470,7 @@ def run_b200(args):
     row_lo = clocks.mark()
     blocks = [timed_block(idx) for idx in cycle_blocks(w0)]            # cycle 0: the blocks after the parity frames
     first_ms = dist_max([float(np.median([b[0] for b in blocks]))], device=devname)[0]
-    nblocks = block_plan(first_ms) if not TINY else 2
+    nblocks = block_plan(first_ms) if not (TINY or NCU_SHORT) else (2 if TINY else 1)
     while len(blocks) < nblocks:
         w, _ = begin_cycle(False)
         for idx in cycle_blocks(w):
@@ -479,7 +482,7 @@ def run_b200(args):
     ms = float(ms_blocks[bmed])
     launches, npts, perr = blocks[bmed][1], blocks[bmed][2], max(b[3] for b in blocks)
     eblocks = []
-    while len(eblocks) < (min(nblocks, 60) if not TINY else 2):
+    while len(eblocks) < (min(nblocks, 60) if not (TINY or NCU_SHORT) else (2 if TINY else 1)):
         w, _ = begin_cycle(False)
         for idx in cycle_blocks(w):
             eblocks.append(e2e_block(idx))
@@ -506,11 +509,11 @@ def run_b200(args):
     prof = tree.profile_read(reset=True)
     tree.profile_enable(False)
     solo = world_size == 1 and not args.no_cpu_baseline
-    frontend = frontend_rows(work, ses, fov, torch, local, F, rank, cpu=solo) if not TINY else None
+    frontend = frontend_rows(work, ses, fov, torch, local, F, rank, cpu=solo) if not (TINY or NCU_SHORT) else None
     stats = tree.stats()
     ses.close()
     tree.close()
-    frontier = frontier_rows(work, torch, local) if (rank == 0 and not TINY) else None
+    frontier = frontier_rows(work, torch, local) if (rank == 0 and not (TINY or NCU_SHORT)) else None
     if rank == 0:
         peaks = {}
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -756,10 +759,12 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--scans", type=int, default=0, help="cfg3/cfg4: number of consecutive scans (0 = the config's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-short", action="store_true", help="profiling runs under ncu: 3 settle frames, one timed block, no extra rows")
     ap.add_argument("--tiny", action="store_true", help="test-only: shrink the workload (not a bench configuration)")
     args = ap.parse_args()
-    global TINY
+    global TINY, NCU_SHORT
     TINY = args.tiny
+    NCU_SHORT = args.ncu_short
     protect_stdout()
     if args.warmup < 3 and args.impl == "b200":
         log("note: timing rules ask for >= 3 warm-up steps")

@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py --config cfg3|cfg4 — BASELINE.json configs[2] and configs[3] at full size.  Not the headline:
+each prints ONE JSON line of its own; the lines of the round are kept under profiles/ and quoted in README / DESIGN §7.
+
+cfg3  Livox HAP narrow-FoV (120 x 25 deg, non-repetitive), 240 000 rays/scan all used as queries, filter_size_map_min = 0.1,
+      extrinsic_est_en = true, max_iteration = 4 (config/hap_livox.yaml:45,54-58), recontructIKdTree every kd_step = 40
+      key frames from the key-frame clouds within 10 m of the newest pose, leaf 0.2 (laserMapping.cpp:612-669,
+      hap_livox.yaml:82-84).  Reports scans/s (device events over the steps), the reconstruct time and the parity of the
+      first frames against the CPU oracle.
+cfg4  Ouster-64 (64 x 1024 rays), 10M-point map, >= 2000 consecutive scans streamed from pinned host buffers through the
+      C ABI (scan upload overlapped, posterior read back every scan): scans/s, p50 / p99 / max per-scan period, device
+      memory high-water (config/mulran.yaml:53-57).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+_WORLD = None      # set before the worker processes are forked (inherited, not pickled)
+_DIRS = {}
+
+
+def _gen_scan(job):
+    """One scan (worker process): ray-cast from the true state with a per-frame seeded generator."""
+    from better_fastlio2_b200 import synth
+    st, model, dirs_seed, seed, max_range = job
+    key = (model, dirs_seed)
+    if key not in _DIRS:
+        _DIRS.clear()
+        _DIRS[key] = synth.lidar_dirs(model, np.random.default_rng(dirs_seed) if dirs_seed is not None else None)
+    rng = np.random.default_rng(seed)
+    return synth.scan_from_pose(_WORLD, st, _DIRS[key], rng, max_range=max_range, min_range=2.0)
+
+
+def gen_scans(world, truths, model, seed, per_frame_dirs=False, max_range=100.0):
+    """Scans of all frames; forked worker processes when the host has the cores for it."""
+    global _WORLD
+    _WORLD = world
+    jobs = [(st, model, (seed * 7919 + k) if per_frame_dirs else None, seed * 100003 + k, max_range) for k, st in enumerate(truths)]
+    ncpu = os.cpu_count() or 1
+    if ncpu >= 8 and len(jobs) >= 16:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(ncpu - 2, 64)) as pool:
+            return pool.map(_gen_scan, jobs, chunksize=4)
+    return [_gen_scan(j) for j in jobs]
+
+
+def pin4(torch, s):
+    b4 = np.zeros((len(s), 4), np.float32)
+    b4[:, :3] = s
+    return torch.from_numpy(b4).pin_memory()
+
+
+def parity_frames(capi, po, synth, work, ds, max_iter, extr, frames, tree, fov_kw):
+    """GPU vs CPU oracle over the first `frames` frames, both from the same freshly built map."""
+    ref = po.make_map(ds=ds, threads=os.cpu_count() or 1)
+    bench.build_map(ref, work["map"])
+    ses = capi.Session(tree, max_scan_points=max(len(s) for s in work["scans"][:frames]), extrinsic_est_en=extr,
+                       max_iterations=max_iter, filter_size_map_min=ds)
+    fov_g = capi.make_fov(**fov_kw)
+    fov_c = po.FovSegment(**fov_kw)
+    pos_lid = np.zeros(3)
+    pg, pc = [], []
+    for k in range(frames):
+        body = work["scans"][k]
+        s_g, _, r = ses.scan_step(fov_g, body, work["priors"][k], work["P"], True)
+        boxes = fov_c.step(pos_lid)
+        if len(boxes):
+            ref.Delete_Point_Boxes(boxes)
+        s_c, _, sc, st, _ = po.esikf_update(work["priors"][k], work["P"], body, ref, max_iter=max_iter, extrinsic_est_en=extr)
+        pos_lid = s_c[0:3] + synth.quat_to_mat(s_c[3:7]) @ s_c[11:14]
+        po.map_incremental(s_c, body, sc, ref, True, ds)
+        pg.append(s_g)
+        pc.append(s_c)
+    par = bench.pose_parity(pg, pc)
+    par["map_size_diff"] = int(abs(tree.validnum() - ref.validnum()))
+    par["what"] = "GPU posterior vs CPU replay (reference ikd-Tree compiled unmodified + restated, unpinned, h_share_model/ESIKF)"
+    ses.close()
+    ref.close()
+    return par
+
+
+# --------------------------------------------------------------------------------------------------------------- cfg3
+def run_cfg3(args):
+    import torch
+    from better_fastlio2_b200 import capi, synth
+    DS3, MAXIT, KD_STEP, RADIUS, LEAF = 0.1, 4, 40, 10.0, 0.2
+    NS = args.scans or 90
+    seed = 3
+    rng = np.random.default_rng(seed)
+    dz = -bench.SENSOR_HEIGHT
+    world = synth.city_world(half_extent=400.0, seed=seed).shifted((0.0, 0.0, dz))
+    truths = [synth.trajectory_state(k, speed=10.0, z=1.8 + dz) for k in range(NS)]
+    t0 = time.perf_counter()
+    scans = gen_scans(world, truths, "hap", seed, per_frame_dirs=True)
+    priors = [synth.perturb_state(st, rng, 0.05, 0.5) for st in truths]
+    # pre-filled map: the forward corridor the narrow field of view sees over the first kd_step frames (afterwards the map
+    # is what recontructIKdTree builds from the key frames)
+    mp = synth.sample_surface_map(world, (60.0, 0.0, 0.0), (110.0, 70.0, 1e3), DS3, rng, zmax=25.0 + dz)
+    bench.log(f"cfg3 workload: {NS} scans of ~{np.mean([len(s) for s in scans]):.0f} pts, map {len(mp)} pts, gen {time.perf_counter() - t0:.1f}s")
+    work = dict(map=mp, scans=scans, priors=priors, truths=truths, P=synth.default_cov())
+    tree = capi.KDTree(voxel_size=DS3, max_points=32 << 20, max_blocks=4 << 20)
+    bench.build_map(tree, mp)
+    fov_kw = dict(cube_len=1000.0, det_range=100.0)
+    out = {"config": {"workload": "cfg3: Livox HAP 120x25 deg, 240k rays/scan (Q-raw), filter_size_map_min 0.1, extrinsic_est_en, "
+                                  "max_iteration 4, recontructIKdTree every 40 key frames (radius 10 m, leaf 0.2)", "n_scans": NS},
+           "metric": "scans/s", "unit": "scans/s", "data": "synthetic", "n_gpus": 1}
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        po.build()
+        out["parity"] = parity_frames(capi, po, synth, work, DS3, MAXIT, True, 6, tree, fov_kw)
+        bench.build_map(tree, mp)     # fresh map for the timed replay
+    nmax = max(len(s) for s in scans)
+    ses = capi.Session(tree, max_scan_points=max(262144, nmax), extrinsic_est_en=True, max_iterations=MAXIT, filter_size_map_min=DS3)
+    fov = capi.make_fov(**fov_kw)
+    stream = torch.cuda.ExternalStream(ses.stream_ptr(), device=torch.device("cuda", 0))
+    dev = []
+    for s in scans:
+        b4 = np.zeros((len(s), 4), np.float32)
+        b4[:, :3] = s
+        dev.append(torch.from_numpy(b4).to("cuda:0"))
+    torch.cuda.synchronize()
+    # key-frame clouds as the node keeps them (PointType records of the undistorted scan, body frame, laserMapping.cpp:756-758)
+    # and their poses (x, y, z, roll, pitch, yaw of the posterior)
+    kf_clouds, kf_poses = [], []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    step_ms, recon_ms, recon_pts, errs, launches = 0.0, [], [], [], 0
+    seg_start = 0
+    ev[0].record(stream)
+    for k in range(NS):
+        st, P = priors[k].copy(), work["P"].copy()
+        ses.scan_set_device(dev[k].data_ptr(), len(scans[k]))
+        r = ses.scan_step_ptr(fov, None, 0, 0, st, P)
+        launches += r.kernel_launches
+        errs.append(float(np.linalg.norm(st[:3] - truths[k][:3])))
+        R = synth.quat_to_mat(st[3:7])
+        roll, pitch, yaw = np.arctan2(R[2, 1], R[2, 2]), -np.arcsin(R[2, 0]), np.arctan2(R[1, 0], R[0, 0])
+        kf_clouds.append(capi.pack_pointtype(scans[k]))
+        kf_poses.append([st[0], st[1], st[2], roll, pitch, yaw])
+        if (k + 1) % KD_STEP == 0:
+            ev[1].record(stream)
+            torch.cuda.synchronize()
+            step_ms += ev[0].elapsed_time(ev[1])
+            near = [i for i in range(len(kf_poses)) if np.linalg.norm(np.array(kf_poses[i][:3]) - np.array(kf_poses[-1][:3])) <= RADIUS]
+            t0 = time.perf_counter()
+            feats = capi.reconstruct_keyframes(tree, [kf_clouds[i] for i in near], [kf_poses[i] for i in near], LEAF)
+            torch.cuda.synchronize()
+            recon_ms.append(1e3 * (time.perf_counter() - t0))
+            recon_pts.append(int(len(feats)))
+            seg_start = k + 1
+            ev[0].record(stream)
+    ev[1].record(stream)
+    torch.cuda.synchronize()
+    step_ms += ev[0].elapsed_time(ev[1])
+    stats = tree.stats()
+    out.update({"value": NS / (step_ms * 1e-3), "ms_per_step": step_ms / NS, "steps": NS, "gpu_launches": launches,
+                "scan_points_mean": float(np.mean([len(s) for s in scans])),
+                "reconstruct": {"every": KD_STEP, "ms": recon_ms, "submap_points": recon_pts,
+                                "what": "recontructIKdTree data path: key-frame clouds (host, 48-B PointType) -> transform -> VoxelGrid(0.2) -> "
+                                        "reconstruct, wall clock incl. the upload"},
+                "pose_err_vs_truth_max_m": max(errs), "map_valid_end": int(stats["valid_points"]), "device_bytes": int(stats["device_bytes"])})
+    ses.close()
+    tree.close()
+    bench.emit(out)
+
+
+# --------------------------------------------------------------------------------------------------------------- cfg4
+def tri(k, period):
+    """Triangular wave 0..period..0 (ping-pong along the street)."""
+    p = k % (2 * period)
+    return p if p <= period else 2 * period - p
+
+
+def run_cfg4(args):
+    import torch
+    from better_fastlio2_b200 import capi, synth
+    DS4, MAXIT = 0.2, 3
+    NS = args.scans or 2000
+    LEG = 360          # frames per leg of the ping-pong (1 m per frame)
+    seed = 4
+    rng = np.random.default_rng(seed)
+    dz = -bench.SENSOR_HEIGHT
+    world = synth.city_world(half_extent=400.0, seed=seed).shifted((0.0, 0.0, dz))
+    truths = [synth.trajectory_state(tri(k, LEG) - LEG // 2, speed=10.0, z=1.8 + dz) for k in range(NS)]
+    t0 = time.perf_counter()
+    scans = gen_scans(world, truths, "os64", seed)
+    priors = [synth.perturb_state(st, rng, 0.05, 0.5) for st in truths]
+    mp = synth.sample_surface_map(world, (0.0, 0.0, 0.0), (LEG / 2 + 105.0, 196.0, 1e3), DS4, rng, zmax=25.0 + dz)   # ~10M points
+    bench.log(f"cfg4 workload: {NS} scans of ~{np.mean([len(s) for s in scans]):.0f} pts, map {len(mp)} pts, gen {time.perf_counter() - t0:.1f}s")
+    work = dict(map=mp, scans=scans, priors=priors, truths=truths, P=synth.default_cov())
+    free0, total = torch.cuda.mem_get_info(0)
+    tree = capi.KDTree(voxel_size=DS4, max_points=32 << 20, max_blocks=4 << 20)
+    bench.build_map(tree, mp)
+    fov_kw = dict(cube_len=1000.0, det_range=100.0)
+    out = {"config": {"workload": "cfg4: Ouster-64 64x1024 rays/scan (Q-raw), 0.2 m voxel, ~10M-pt map, max_iteration 3, sustained "
+                                  "streaming from pinned host buffers, ping-pong trajectory (every place revisited)", "n_scans": NS},
+           "metric": "scans/s", "unit": "scans/s", "data": "synthetic", "n_gpus": 1, "map_points_in": int(len(mp)),
+           "map_valid_start": int(tree.validnum())}
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        po.build()
+        out["parity"] = parity_frames(capi, po, synth, work, DS4, MAXIT, False, 5, tree, fov_kw)
+        bench.build_map(tree, mp)
+    nmax = max(len(s) for s in scans)
+    ses = capi.Session(tree, max_scan_points=max(65536, nmax), max_iterations=MAXIT, filter_size_map_min=DS4)
+    fov = capi.make_fov(**fov_kw)
+    pin = [pin4(torch, s) for s in scans]
+    torch.cuda.synchronize()
+    sts = [p.copy() for p in priors]
+    Ps = [work["P"].copy() for _ in range(NS)]
+    lat = np.empty(NS)
+    free_min = torch.cuda.mem_get_info(0)[0]
+    launches = 0
+    for k in range(min(10, NS)):     # warm-up on the first frames (graphs, clocks); they are replayed in the timed run
+        st, P = priors[k].copy(), work["P"].copy()
+        ses.scan_step_ptr(fov, pin[k].data_ptr(), len(scans[k]), 16, st, P)
+    bench.build_map(tree, mp)
+    fov = capi.make_fov(**fov_kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ses.scan_prefetch_ptr(pin[0].data_ptr(), len(scans[0]), 16)
+    tp = t0
+    for k in range(NS):
+        ses.scan_step_begin(fov, sts[k], Ps[k], True)
+        if k + 1 < NS:
+            ses.scan_prefetch_ptr(pin[k + 1].data_ptr(), len(scans[k + 1]), 16)
+        r = ses.scan_step_finish(fov, sts[k], Ps[k])
+        launches += r.kernel_launches
+        tn = time.perf_counter()
+        lat[k] = tn - tp
+        tp = tn
+        if (k & 127) == 0:
+            free_min = min(free_min, torch.cuda.mem_get_info(0)[0])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    stats = tree.stats()
+    errs = [float(np.linalg.norm(sts[k][:3] - truths[k][:3])) for k in range(NS)]
+    q = NS // 4
+    out.update({"value": NS / dt, "ms_per_step": 1e3 * dt / NS, "steps": NS, "gpu_launches": launches,
+                "scan_points_mean": float(np.mean([len(s) for s in scans])),
+                "latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3),
+                               "max": float(lat.max() * 1e3), "what": "posterior-to-posterior period of the streaming loop (host clock)"},
+                "ms_per_step_by_quarter": [float(1e3 * lat[i * q:(i + 1) * q].mean()) for i in range(4)],
+                "e2e": {"value": NS / dt, "unit": "scans/s", "h2d_bytes_per_step": int(16 * np.mean([len(s) for s in scans])),
+                        "d2h_bytes_per_step": 3240},
+                "pose_err_vs_truth_max_m": max(errs), "map_valid_end": int(stats["valid_points"]),
+                "map_stats": {k: stats[k] for k in ("blocks_in_use", "overflow_in_use", "coarse_cells", "hash_tombstones")},
+                "device_bytes_library": int(stats["device_bytes"]),
+                "device_bytes_high_water": int(free0 - free_min), "device_bytes_total": int(total)})
+    ses.close()
+    tree.close()
+    bench.emit(out)
+
+
+def run(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if args.config == "cfg3":
+        run_cfg3(args)
+    else:
+        run_cfg4(args)

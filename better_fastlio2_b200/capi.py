@@ -79,6 +79,8 @@ EXPORTS = [
     "flb_frontend_create", "flb_frontend_destroy", "flb_frontend_upload", "flb_frontend_undistort",
     "flb_frontend_voxel_filter", "flb_frontend_process", "flb_frontend_download_undistorted", "flb_frontend_download_down",
     "flb_frontend_points_to_world", "flb_voxel_grid_filter", "flb_map_reconstruct_keyframes",
+    "flb_map_build_pt", "flb_map_reconstruct_pt", "flb_map_add_points_pt", "flb_map_nearest_search_xyzi",
+    "flb_map_box_search_xyzi", "flb_map_radius_search_xyzi", "flb_map_flatten_xyzi", "flb_scan_upload_pt",
 ]
 
 
@@ -101,6 +103,14 @@ def lib():
         L.flb_map_build.argtypes = [vp, fp, C.c_int, C.c_int]
         L.flb_map_reconstruct.argtypes = [vp, fp, C.c_int, C.c_int]
         L.flb_map_add_points.argtypes = [vp, fp, C.c_int, C.c_int, C.c_int, ip]
+        L.flb_map_build_pt.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        L.flb_map_reconstruct_pt.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        L.flb_map_add_points_pt.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+        L.flb_map_nearest_search_xyzi.argtypes = [vp, fp, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp, vp]
+        L.flb_map_box_search_xyzi.argtypes = [vp, fp, fp, C.c_int, ip]
+        L.flb_map_radius_search_xyzi.argtypes = [vp, fp, C.c_float, fp, C.c_int, ip]
+        L.flb_map_flatten_xyzi.argtypes = [vp, fp, C.c_int, ip]
+        L.flb_scan_upload_pt.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.flb_map_delete_boxes.argtypes = [vp, fp, C.c_int, ip]
         L.flb_map_delete_points.argtypes = [vp, fp, C.c_int, C.c_int, ip]
         L.flb_map_nearest_search.argtypes = [vp, fp, C.c_int, C.c_int, C.c_int, C.c_float, fp, fp, vp]
@@ -208,6 +218,45 @@ class KDTree:
         n = C.c_int(0)
         _chk(lib().flb_map_add_points(self.h, _p(pts), len(pts), pts.strides[0], 1 if downsample_on else 0, C.byref(n)))
         return n.value
+
+    # PointType-aware variants: (n, 4) arrays of x, y, z, intensity (ikd_Tree.h:64-86 keeps whole records)
+    def Build_xyzi(self, pts4):
+        a = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+        _chk(lib().flb_map_build_pt(self.h, _p(a), len(a), 16, 12))
+
+    def Add_Points_xyzi(self, pts4, downsample_on):
+        a = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+        n = C.c_int(0)
+        _chk(lib().flb_map_add_points_pt(self.h, _p(a), len(a), 16, 12, 1 if downsample_on else 0, C.byref(n)))
+        return n.value
+
+    def Build_pointtype(self, points48):
+        a = np.ascontiguousarray(points48, np.float32).reshape(-1, 12)
+        _chk(lib().flb_map_build_pt(self.h, _p(a), len(a), POINT_STRIDE, OFF_INTENSITY))
+
+    def Nearest_Search_xyzi(self, q, k=5, max_dist=0.0):
+        q = _xyz(q)
+        n = len(q)
+        out = np.empty((n, k, 4), np.float32)
+        d2 = np.empty((n, k), np.float32)
+        cnt = np.empty(n, np.int32)
+        _chk(lib().flb_map_nearest_search_xyzi(self.h, _p(q), n, q.strides[0], k, float(max_dist), _p(out), _p(d2), _p(cnt)))
+        return out, d2, cnt
+
+    def flatten_xyzi(self):
+        n = C.c_int(0)
+        _chk(lib().flb_map_flatten_xyzi(self.h, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        n2 = C.c_int(0)
+        _chk(lib().flb_map_flatten_xyzi(self.h, _p(out), n.value, C.byref(n2)))
+        return out[:min(n.value, n2.value)].copy()
+
+    def Box_Search_xyzi(self, box6, cap=1 << 20):
+        b = np.ascontiguousarray(box6, np.float32).reshape(6)
+        out = np.empty((cap, 4), np.float32)
+        n = C.c_int(0)
+        _chk(lib().flb_map_box_search_xyzi(self.h, _p(b), _p(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
 
     def Delete_Point_Boxes(self, boxes):
         b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
@@ -323,6 +372,12 @@ class Session:
         body = _xyz(body)
         _chk(lib().flb_scan_upload(self.h, _p(body), len(body), body.strides[0]))
         self.n = len(body)
+
+    def scan_upload_xyzi(self, body4):
+        """feats_down_body with intensity: (n, 4) float32 x, y, z, intensity (travels into the map, laserMapping.cpp:1101-1110)."""
+        a = np.ascontiguousarray(body4, np.float32).reshape(-1, 4)
+        self.n = len(a)
+        _chk(lib().flb_scan_upload_pt(self.h, _p(a), len(a), 16, 12))
 
     def scan_prefetch_ptr(self, ptr, n, stride):
         """Start the async upload of the NEXT scan (raw host pointer, pinned recommended)."""

@@ -326,6 +326,7 @@ __device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double*
 // Load the propagated state / covariance for a new scan.
 // staging layout: x0[26] | P0[529] | n | flg_EKF_inited   (all doubles, so one H2D copy carries a scan's inputs)
 __global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage, int* work_counts) {
+  pdl_sync();
   FLB_TRACE_BEGIN(0);
   const double* x0 = stage;
   const double* P0 = stage + 26;
@@ -367,6 +368,7 @@ struct EsikfScratch {
 
 template <int MD>
 __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl* c, EsikfScratch* sc) {
+  pdl_sync();
   using namespace dev;
   __shared__ double P[NDOF * NDOF], L[144], T[144];
   __shared__ double dx[NDOF], J3a[9], J3b[9], J2[4], Nx[6], Mx[6], xs[26], xps[26];
@@ -430,6 +432,7 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
 template <int MD>
 __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, const double* __restrict__ partial, int nblocks,
                                                                     const EsikfScratch* __restrict__ sc) {
+  pdl_sync();
   using namespace dev;
   __shared__ double acc[96], acc2[96];
   __shared__ double P[NDOF * NDOF], L[NDOF * NDOF], T[144], Q[NDOF * 12], Y[156];

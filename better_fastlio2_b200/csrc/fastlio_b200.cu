@@ -9,6 +9,7 @@
 #include "esikf_host.hpp"
 
 #include <cub/device/device_scan.cuh>
+#include <chrono>
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
@@ -49,6 +50,27 @@ extern "C" int flb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+// Kernel launch of the scan sequence.  FLB_PDL=1 adds the programmatic-stream-serialization attribute (programmatic
+// dependent launch: a kernel's launch overlaps its predecessor's tail; the kernels call pdl_sync() before touching
+// anything; under stream capture the attribute becomes a programmatic graph edge).  Measured on B200 inside the captured
+// scan graph (profiles/r2_pdl_ab.txt): kernel-to-kernel gaps and the step's device span unchanged (260.7 vs 261.0 us),
+// cudaGraphLaunch 12.7 -> 22.3 us on the host — so it is OFF by default and kept only as an A/B switch.
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("FLB_PDL"); return e && atoi(e) != 0; }();
+  return on;
+}
+template <typename... P, typename... A>
+static cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
 }
 
 static inline uint32_t next_pow2(uint64_t v) {
@@ -208,6 +230,8 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   rc |= dev_alloc(m, (void**)&d.bslot, sizeof(uint32_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.slots, sizeof(float4) * 64 * (size_t)d.block_cap);
   rc |= dev_alloc(m, (void**)&d.ovf, sizeof(float4) * (size_t)d.ovf_cap);
+  rc |= dev_alloc(m, (void**)&d.sint, sizeof(float) * 64 * (size_t)d.block_cap);
+  rc |= dev_alloc(m, (void**)&d.oint, sizeof(float) * (size_t)d.ovf_cap);
   rc |= dev_alloc(m, (void**)&d.bkey, sizeof(uint64_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.brel, sizeof(uint64_t) * d.block_cap);
   rc |= dev_alloc(m, (void**)&d.free_blk, sizeof(uint32_t) * d.block_cap);
@@ -241,7 +265,7 @@ static void map_release(flb_map* m) {
   Q(cudaSetDevice(m->cfg.device));
   if (m->stream) Q(cudaStreamSynchronize(m->stream));
   MapDev& d = m->d;
-  void* ptrs[] = {d.clist, d.hent, d.bslot, d.slots, d.ovf, d.bkey, d.brel, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
+  void* ptrs[] = {d.clist, d.hent, d.bslot, d.slots, d.sint, d.oint, d.ovf, d.bkey, d.brel, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
                   m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
   for (void* p : ptrs) if (p) Q(cudaFree(p));
   if (m->h_counters) Q(cudaFreeHost(m->h_counters));
@@ -264,11 +288,13 @@ extern "C" int flb_map_set_downsample_param(flb_map* m, float v) {
 }
 extern "C" int flb_map_has_root(const flb_map* m) { return m && m->has_root ? 1 : 0; }
 
-// host strided xyz -> device float4 staging
-static int upload_points(flb_map* m, const float* xyz, int n, int stride) {
+// host strided points -> device float4 staging (x, y, z, intensity).  off_i: byte offset of the intensity inside a record,
+// < 0 = none (0).  16-byte records are taken as (x, y, z, intensity) verbatim.
+static int upload_points(flb_map* m, const void* pts, int n, int stride, int off_i = -1) {
   if (n <= 0) return 0;
-  if (!xyz) return set_err("null point buffer");
+  if (!pts) return set_err("null point buffer");
   if (stride < 12) return set_err("stride_bytes must be >= 12");
+  if (off_i >= 0 && off_i + 4 > stride) return set_err("intensity offset %d outside the %d-byte record", off_i, stride);
   if (n > m->stage_cap) {
     if (m->stage) cudaFree(m->stage);
     m->stage = nullptr;
@@ -277,11 +303,11 @@ static int upload_points(flb_map* m, const float* xyz, int n, int stride) {
     CU(cudaMalloc((void**)&m->stage, sizeof(float4) * (size_t)cap));
     m->stage_cap = cap;
   }
-  if (stride == 16) {
-    CU(cudaMemcpyAsync(m->stage, xyz, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+  if (stride == 16 && (off_i < 0 || off_i == 12)) {
+    CU(cudaMemcpyAsync(m->stage, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
     return 0;
   }
-  const size_t bytes = (size_t)(n - 1) * stride + 12;
+  const size_t bytes = (size_t)(n - 1) * stride + (size_t)std::max(12, off_i + 4);
   if (bytes > m->raw_cap) {
     if (m->raw) cudaFree(m->raw);
     m->raw = nullptr;
@@ -290,8 +316,8 @@ static int upload_points(flb_map* m, const float* xyz, int n, int stride) {
     CU(cudaMalloc((void**)&m->raw, cap));
     m->raw_cap = cap;
   }
-  CU(cudaMemcpyAsync(m->raw, xyz, bytes, cudaMemcpyHostToDevice, m->stream));
-  k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(m->raw, stride, m->stage, n);
+  CU(cudaMemcpyAsync(m->raw, pts, bytes, cudaMemcpyHostToDevice, m->stream));
+  k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(m->raw, stride, off_i, m->stage, n);
   m->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -316,30 +342,36 @@ static int maybe_rehash(flb_map* m);
 // Insert device points. mode 0: verbatim (Build / Add_Points(false)); 1: downsample (Add_Points(true));
 // 2: classified (map_incremental: cls 1 -> downsample, cls 2 -> verbatim). Asynchronous on m->stream.
 static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode, const int* skip = nullptr,
-                         const int* n_dev = nullptr) {
+                         const int* n_dev = nullptr, bool prefused = false) {
   // n_dev != nullptr: n is an upper bound (capacity) used for launch geometry, the real count is read on the device
   if (n <= 0) return 0;
   const int g = grid_for(n, 256, m->sm_count * 8);
   cudaStream_t st = m->stream;
   const unsigned char* c = (mode == 2) ? cls : nullptr;
   ProfScope ps(m, FLB_K_INSERT);
-  k_touch_blocks<<<g, 256, 0, st>>>(m->d, pts, c, (1 << 1) | (1 << 2), n, skip, n_dev);
-  m->launches++;
+  // prefused: k_classify already touched the blocks and scattered the downsampled class into the (cleared) scratch hash
+  if (!prefused) {
+    launch_k(k_touch_blocks, g, 256, 0, st, m->d, pts, c, (1 << 1) | (1 << 2), n, skip, n_dev);
+    m->launches++;
+  }
   if (mode == 1 || mode == 2) {
-    if (ensure_scratch(m, n)) return 1;
     const uint32_t sc = next_pow2((uint64_t)std::max(n, 512) * 2);
-    if (!m->scratch_clean) {
-      CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
-      CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
+    if (!prefused) {
+      if (ensure_scratch(m, n)) return 1;
+      if (!m->scratch_clean) {
+        CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc, st));
+        CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc, st));
+      }
+      launch_k(k_ds_scatter, g, 256, 0, st, m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
+      m->launches++;
     }
     m->scratch_clean = false;
-    k_ds_scatter<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
-    k_ds_apply<<<g, 256, 0, st>>>(m->d, pts, c, n, m->skeys, m->sbest, sc - 1, skip, n_dev);
-    m->launches += 2;
+    launch_k(k_ds_apply, g, 256, 0, st, m->d, pts, c, n, (const uint64_t*)m->skeys, (const unsigned long long*)m->sbest, sc - 1, skip, n_dev);
+    m->launches++;
   }
   if (mode == 0 || mode == 2) {
-    k_append_points<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip, n_dev);
-    k_relocate_chains<<<g, 256, 0, st>>>(m->d, pts, c, 2, n, skip, n_dev);
+    launch_k(k_append_points, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev);
+    launch_k(k_relocate_chains, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev);
     m->launches += 2;
   }
   CU(cudaGetLastError());
@@ -352,30 +384,37 @@ static int zero_scratch_counters(flb_map* m) {
   return 0;
 }
 
-extern "C" int flb_map_build(flb_map* m, const float* xyz, int n, int stride) {
+extern "C" int flb_map_build_pt(flb_map* m, const void* pts, int n, int stride, int off_intensity) {
   if (!m) return set_err("null map");
   if (n < 0) return set_err("negative point count");
   CU(cudaSetDevice(m->cfg.device));
   if (map_reset_storage(m)) return 1;
   if (n == 0) return 0;  // Build with an empty cloud leaves Root_Node == nullptr (ikd_Tree.cpp:357)
-  if (upload_points(m, xyz, n, stride)) return 1;
+  if (upload_points(m, pts, n, stride, off_intensity)) return 1;
   if (insert_device(m, m->stage, nullptr, n, 0)) return 1;
   return fetch_counters(m);
 }
-extern "C" int flb_map_reconstruct(flb_map* m, const float* xyz, int n, int stride) { return flb_map_build(m, xyz, n, stride); }
+extern "C" int flb_map_build(flb_map* m, const float* xyz, int n, int stride) { return flb_map_build_pt(m, xyz, n, stride, -1); }
+extern "C" int flb_map_reconstruct(flb_map* m, const float* xyz, int n, int stride) { return flb_map_build_pt(m, xyz, n, stride, -1); }
+extern "C" int flb_map_reconstruct_pt(flb_map* m, const void* pts, int n, int stride, int off_intensity) {
+  return flb_map_build_pt(m, pts, n, stride, off_intensity);
+}
 
-extern "C" int flb_map_add_points(flb_map* m, const float* xyz, int n, int stride, int downsample_on, int* n_added) {
+extern "C" int flb_map_add_points_pt(flb_map* m, const void* pts, int n, int stride, int off_intensity, int downsample_on, int* n_added) {
   if (!m) return set_err("null map");
   if (n_added) *n_added = 0;
   if (n <= 0) return 0;
   CU(cudaSetDevice(m->cfg.device));
-  if (upload_points(m, xyz, n, stride)) return 1;
+  if (upload_points(m, pts, n, stride, off_intensity)) return 1;
   if (zero_scratch_counters(m)) return 1;
   if (insert_device(m, m->stage, nullptr, n, downsample_on ? 1 : 0)) return 1;
   if (fetch_counters(m)) return 1;
   // reference return value: tmp_counter counts downsample add ops only (ikd_Tree.cpp:447,457,488)
   if (n_added) *n_added = downsample_on ? m->h_counters[CNT_SCRATCH0] : 0;
   return 0;
+}
+extern "C" int flb_map_add_points(flb_map* m, const float* xyz, int n, int stride, int downsample_on, int* n_added) {
+  return flb_map_add_points_pt(m, xyz, n, stride, -1, downsample_on, n_added);
 }
 
 static int upload_params(flb_map* m, const float* host, int nfloats) {
@@ -474,11 +513,10 @@ static int launch_knn(flb_map* m, KnnArgs a) {
     a.work_ticket = m->d_misc + 13;
     CU(cudaMemsetAsync(a.work_count, 0, 2 * sizeof(int), m->stream));
   }
-  k_knn_stencil<K><<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+  launch_k(k_knn_stencil<K>, (a.n + 127) / 128, 128, 0, m->stream, a);
   // the fallback grid is sized for the typical <2 % unresolved share; it loops over the list
   // all CTAs resident; they loop over the list.  Lanes per query: 8 (four queries per warp) or a whole warp
-  if (K <= 8 && m->knn_group == 8) k_knn<K, (K <= 8 ? 8 : 32)><<<m->sm_count * KNN_MIN_CTAS, KNN_THREADS, 0, m->stream>>>(a);
-  else k_knn<K, 32><<<m->sm_count * KNN_MIN_CTAS, KNN_THREADS, 0, m->stream>>>(a);
+  launch_k(k_knn<K>, m->sm_count * KNN_MIN_CTAS, KNN_THREADS, 0, m->stream, a);
   m->launches += 2;
   return 0;
 }
@@ -494,8 +532,8 @@ static int ensure_outbuf(flb_map* m, int n) {
   return 0;
 }
 
-extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, int stride, int k, float max_dist,
-                                      float* out_xyz, float* out_d2, int* out_cnt) {
+static int nearest_search_impl(flb_map* m, const float* q_xyz, int nq, int stride, int k, float max_dist, float* out_pts, int out_w,
+                               float* out_d2, int* out_cnt) {
   if (!m) return set_err("null map");
   if (k < 1 || k > 20) return set_err("Nearest_Search: k must be in [1,20]");
   if (nq <= 0) return 0;
@@ -504,6 +542,7 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
   const int K = k <= 5 ? 5 : 20;
   if (ensure_outbuf(m, nq * K)) return 1;
   unsigned char* dcnt = nullptr;
+  float* dint = nullptr;
   CU(cudaMalloc((void**)&dcnt, nq));
   KnnArgs a;
   a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt;
@@ -514,10 +553,22 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
   cudaError_t le = lrc ? cudaErrorUnknown : cudaGetLastError();
   std::vector<float4> h((size_t)nq * K);
   std::vector<unsigned char> hc(nq);
+  std::vector<float> hi;
+  if (le == cudaSuccess && out_w == 4 && out_pts) {
+    // the neighbours' intensities (the reference returns whole PointType records, ikd_Tree.cpp:391-395)
+    hi.resize((size_t)nq * K);
+    le = cudaMalloc((void**)&dint, sizeof(float) * hi.size());
+    if (le == cudaSuccess) {
+      k_lookup_intensity<<<grid_for(nq * K, 256, m->sm_count * 8), 256, 0, m->stream>>>(m->d, m->outbuf, dint, nq * K);
+      m->launches++;
+      le = cudaMemcpyAsync(hi.data(), dint, sizeof(float) * hi.size(), cudaMemcpyDeviceToHost, m->stream);
+    }
+  }
   if (le == cudaSuccess) le = cudaMemcpyAsync(h.data(), m->outbuf, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost, m->stream);
   if (le == cudaSuccess) le = cudaMemcpyAsync(hc.data(), dcnt, nq, cudaMemcpyDeviceToHost, m->stream);
   if (le == cudaSuccess) le = cudaStreamSynchronize(m->stream);
   cudaFree(dcnt);
+  if (dint) cudaFree(dint);
   if (le != cudaSuccess) return set_err("nearest_search failed: %s", cudaGetErrorString(le));
   for (int i = 0; i < nq; ++i) {
     const int c = std::min<int>(hc[i], k);
@@ -525,18 +576,28 @@ extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, in
     for (int j = 0; j < k; ++j) {
       const float4 v = h[(size_t)j * nq + i];
       const bool ok = j < c;
-      if (out_xyz) {
-        out_xyz[((size_t)i * k + j) * 3 + 0] = ok ? v.x : NAN;
-        out_xyz[((size_t)i * k + j) * 3 + 1] = ok ? v.y : NAN;
-        out_xyz[((size_t)i * k + j) * 3 + 2] = ok ? v.z : NAN;
+      if (out_pts) {
+        float* o = out_pts + ((size_t)i * k + j) * out_w;
+        o[0] = ok ? v.x : NAN;
+        o[1] = ok ? v.y : NAN;
+        o[2] = ok ? v.z : NAN;
+        if (out_w == 4) o[3] = ok ? hi[(size_t)j * nq + i] : NAN;
       }
       if (out_d2) out_d2[(size_t)i * k + j] = ok ? v.w : INFINITY;
     }
   }
   return 0;
 }
+extern "C" int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, int stride, int k, float max_dist,
+                                      float* out_xyz, float* out_d2, int* out_cnt) {
+  return nearest_search_impl(m, q_xyz, nq, stride, k, max_dist, out_xyz, 3, out_d2, out_cnt);
+}
+extern "C" int flb_map_nearest_search_xyzi(flb_map* m, const float* q_xyz, int nq, int stride, int k, float max_dist,
+                                           float* out_xyzi, float* out_d2, int* out_cnt) {
+  return nearest_search_impl(m, q_xyz, nq, stride, k, max_dist, out_xyzi, 4, out_d2, out_cnt);
+}
 
-static int collect_common(flb_map* m, int mode, const float* params, int nparams, float* out_xyz, int cap, int* n_found) {
+static int collect_common(flb_map* m, int mode, const float* params, int nparams, float* out_xyz, int cap, int* n_found, int out_w = 3) {
   if (n_found) *n_found = 0;
   CU(cudaSetDevice(m->cfg.device));
   if (fetch_counters(m)) return 1;
@@ -558,9 +619,23 @@ static int collect_common(flb_map* m, int mode, const float* params, int nparams
   if (w > 0) {
     std::vector<float4> h(w);
     CU(cudaMemcpy(h.data(), m->outbuf, sizeof(float4) * w, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < w; ++i) { out_xyz[3 * i] = h[i].x; out_xyz[3 * i + 1] = h[i].y; out_xyz[3 * i + 2] = h[i].z; }
+    if (out_w == 4) memcpy(out_xyz, h.data(), sizeof(float4) * (size_t)w);
+    else for (int i = 0; i < w; ++i) { out_xyz[3 * i] = h[i].x; out_xyz[3 * i + 1] = h[i].y; out_xyz[3 * i + 2] = h[i].z; }
   }
   return 0;
+}
+extern "C" int flb_map_flatten_xyzi(flb_map* m, float* out_xyzi, int cap, int* n) {
+  if (!m) return set_err("null map");
+  return collect_common(m, 0, nullptr, 0, out_xyzi, cap, n, 4);
+}
+extern "C" int flb_map_box_search_xyzi(flb_map* m, const float* box6, float* out_xyzi, int cap, int* n_found) {
+  if (!m || !box6) return set_err("null argument");
+  return collect_common(m, 1, box6, 6, out_xyzi, cap, n_found, 4);
+}
+extern "C" int flb_map_radius_search_xyzi(flb_map* m, const float* c, float radius, float* out_xyzi, int cap, int* n_found) {
+  if (!m || !c) return set_err("null argument");
+  const float p[4] = {c[0], c[1], c[2], radius};
+  return collect_common(m, 2, p, 4, out_xyzi, cap, n_found, 4);
 }
 extern "C" int flb_map_flatten(flb_map* m, float* out_xyz, int cap, int* n) {
   if (!m) return set_err("null map");
@@ -689,6 +764,11 @@ struct flb_session {
   cudaGraphExec_t graph_alt[2] = {nullptr, nullptr};  // the same sequences captured for the other body buffer
   int graph_kernels[2] = {0, 0}, graph_kernels_alt[2] = {0, 0};
   int graph_gen = -1;            // flb_map::gen the graphs were captured at
+  // FLB_HOST_TIMING=1: where the host side of a step goes (printed when the session is destroyed)
+  bool host_timing = false;
+  double ht_begin = 0, ht_launch = 0, ht_wait = 0, ht_finish = 0, ht_between = 0;
+  long ht_n = 0;
+  std::chrono::steady_clock::time_point ht_last_finish{};
   bool use_graph = true;
   // double-buffered scan upload (flb_scan_prefetch)
   float4* body_alt = nullptr;
@@ -699,6 +779,7 @@ struct flb_session {
   int pending_n = -1;            // >= 0: a prefetched scan waits in body_alt
   // flb_scan_step_begin / _finish
   bool step_pending = false, step_device = false;
+  bool flags_clean = false;      // sel / cnt hold their per-scan initial values (see scan_reset)
   int step_l0 = 0, step_deleted = 0, step_flg = 1;
   double step_x[26], step_P[NDOF * NDOF];
 };
@@ -745,6 +826,7 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   A((void**)&s->ctl, sizeof(EsikfCtl));
   A((void**)&s->d_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
   A((void**)&s->d_scr, sizeof(EsikfScratch));
+  if (e == cudaSuccess) e = cudaMemset(s->d_cnt2, 0, sizeof(int) * 8);   // [0..1] map_incremental counts
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ctl, sizeof(EsikfCtl));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
@@ -776,12 +858,17 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
     e = cudaMemcpy(s->ctl, s->h_ctl, sizeof(EsikfCtl), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) { flb_session_destroy(s); return set_err("flb_session_create: %s", cudaGetErrorString(e)); }
+  if (const char* ht = getenv("FLB_HOST_TIMING")) s->host_timing = atoi(ht) != 0;
   *out = s;
   return 0;
 }
 
 extern "C" void flb_session_destroy(flb_session* s) {
   if (!s) return;
+  if (s->host_timing && s->ht_n > 0)
+    fprintf(stderr, "[fastlio_b200] host timing over %ld steps (us/step): begin() %.1f (of which graph launch %.1f), finish(): wait %.1f + rest %.1f, "
+            "caller between finish and next begin %.1f\n", s->ht_n, 1e6 * s->ht_begin / s->ht_n, 1e6 * s->ht_launch / s->ht_n,
+            1e6 * s->ht_wait / s->ht_n, 1e6 * s->ht_finish / s->ht_n, 1e6 * s->ht_between / s->ht_n);
   Q(cudaSetDevice(s->map->cfg.device));
   Q(cudaStreamSynchronize(s->map->stream));
   if (s->side) Q(cudaStreamSynchronize(s->side));
@@ -819,26 +906,36 @@ extern "C" int flb_session_sync(flb_session* s) {
   return 0;
 }
 
+static int scan_flags_reset(flb_session* s) {
+  // memset(point_selected_surf, true) (laserMapping.cpp:2131); Nearest_Points empty
+  CU(cudaMemsetAsync(s->sel, 1, (size_t)std::max(s->n, 1), s->map->stream));
+  CU(cudaMemsetAsync(s->cnt, 0, (size_t)std::max(s->n, 1), s->map->stream));
+  s->flags_clean = true;
+  return 0;
+}
 static int scan_reset(flb_session* s, int n) {
   s->n = n;
   s->have_pass = false;
-  // memset(point_selected_surf, true) (laserMapping.cpp:2131); Nearest_Points empty
-  CU(cudaMemsetAsync(s->sel, 1, (size_t)std::max(n, 1), s->map->stream));
-  CU(cudaMemsetAsync(s->cnt, 0, (size_t)std::max(n, 1), s->map->stream));
+  s->flags_clean = false;
+  // The device-driven sequence always starts with a search pass (esekfom.hpp:1636: converge = true), which rewrites cnt
+  // (k_knn_stencil) and sel (k_residual) for every point: the two memsets are only needed by the host-driven entry points
+  // (flb_pass may be asked for a cached pass first), which request them on demand.
+  if (!s->device_update) return scan_flags_reset(s);
   return 0;
 }
 
-extern "C" int flb_scan_upload(flb_session* s, const float* xyz, int n, int stride) {
+extern "C" int flb_scan_upload_pt(flb_session* s, const void* pts, int n, int stride, int off_i) {
   if (!s) return set_err("null session");
   if (n < 0 || n > s->cap) return set_err("scan of %d points exceeds max_scan_points=%d", n, s->cap);
-  if (n > 0 && (!xyz || stride < 12)) return set_err("bad scan buffer");
+  if (n > 0 && (!pts || stride < 12)) return set_err("bad scan buffer");
+  if (off_i >= 0 && off_i + 4 > stride) return set_err("intensity offset %d outside the %d-byte record", off_i, stride);
   CU(cudaSetDevice(s->map->cfg.device));
   flb_map* m = s->map;
   if (n > 0) {
-    if (stride == 16) {
-      CU(cudaMemcpyAsync(s->body, xyz, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    if (stride == 16 && (off_i < 0 || off_i == 12)) {
+      CU(cudaMemcpyAsync(s->body, pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
     } else {
-      const size_t bytes = (size_t)(n - 1) * stride + 12;
+      const size_t bytes = (size_t)(n - 1) * stride + (size_t)std::max(12, off_i + 4);
       if (bytes > s->raw_cap) {
         if (s->raw) cudaFree(s->raw);
         s->raw = nullptr; s->raw_cap = 0;
@@ -846,14 +943,16 @@ extern "C" int flb_scan_upload(flb_session* s, const float* xyz, int n, int stri
         CU(cudaMalloc((void**)&s->raw, rc));
         s->raw_cap = rc;
       }
-      CU(cudaMemcpyAsync(s->raw, xyz, bytes, cudaMemcpyHostToDevice, m->stream));
-      k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(s->raw, stride, s->body, n);
+      CU(cudaMemcpyAsync(s->raw, pts, bytes, cudaMemcpyHostToDevice, m->stream));
+      k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, m->stream>>>(s->raw, stride, off_i, s->body, n);
       m->launches++;
       CU(cudaGetLastError());
     }
   }
   return scan_reset(s, n);
 }
+// (the 4th float of a 16-byte record is carried as the point's intensity into the map; other strides: no intensity)
+extern "C" int flb_scan_upload(flb_session* s, const float* xyz, int n, int stride) { return flb_scan_upload_pt(s, xyz, n, stride, -1); }
 
 extern "C" int flb_scan_prefetch(flb_session* s, const float* xyz, int n, int stride) {
   if (!s) return set_err("null session");
@@ -874,7 +973,7 @@ extern "C" int flb_scan_prefetch(flb_session* s, const float* xyz, int n, int st
         s->raw_alt_cap = std::max(bytes, (size_t)1 << 20);
       }
       CU(cudaMemcpyAsync(s->raw_alt, xyz, bytes, cudaMemcpyHostToDevice, s->copy_stream));
-      k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, s->copy_stream>>>(s->raw_alt, 12, s->body_alt, n);
+      k_pack_points<<<grid_for(n, 256, m->sm_count * 8), 256, 0, s->copy_stream>>>(s->raw_alt, 12, -1, s->body_alt, n);
       m->launches++;
       CU(cudaGetLastError());
     }
@@ -974,6 +1073,7 @@ extern "C" int flb_pass(flb_session* s, const double* state26, int search, flb_p
   CU(cudaSetDevice(s->map->cfg.device));
   memset(out, 0, sizeof(*out));
   if (s->n <= 0) { out->valid = 0; return 0; }
+  if (!s->flags_clean && !s->have_pass && scan_flags_reset(s)) return 1;
   if (enqueue_pass(s, state26, search)) return 1;
   CU(cudaStreamSynchronize(s->map->stream));
   unpack_result(s->h_out, out);
@@ -1024,6 +1124,7 @@ extern "C" int flb_pass_rows(flb_session* s, double* hx, int ld, double* h, int 
 
 static int run_update(flb_session* s, double* state26, double* P, flb_update_stats* stats) {
   flb_map* m = s->map;
+  if (!s->flags_clean && scan_flags_reset(s)) return 1;
   host::IteratedUpdate u(state26, P, s->cfg.laser_point_cov, s->cfg.max_iterations, s->cfg.limit);
   int passes = 0, searches = 0, lastM = 0;
   double lastres = 0;
@@ -1084,7 +1185,7 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
   const bool md12 = s->cfg.extrinsic_est_en != 0;   // measured subspace: 12 columns with extrinsic estimation, else 6
   const int cap = s->cap;
   CU(cudaMemcpyAsync(s->d_x0P0, s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2), cudaMemcpyHostToDevice, st));
-  k_esikf_begin<<<1, 256, 0, st>>>(s->ctl, s->d_x0P0, m->d_misc + 16);
+  launch_k(k_esikf_begin, 1, 256, 0, st, s->ctl, (const double*)s->d_x0P0, m->d_misc + 16);
   m->launches++;
   for (int p = 0; p <= s->cfg.max_iterations; ++p) {
     if (overlap) {
@@ -1121,15 +1222,15 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
       ProfScope ps(m, FLB_K_RESIDUAL);
       MeasArgs ma = meas_args(s, PoseDev{}, 0);
       ma.ctl = s->ctl;
-      if (s->cfg.extrinsic_est_en) k_residual<true><<<s->res_grid, MEAS_THREADS, meas_smem_bytes<true>(), st>>>(ma);
-      else k_residual<false><<<s->res_grid, MEAS_THREADS, meas_smem_bytes<false>(), st>>>(ma);
+      if (s->cfg.extrinsic_est_en) launch_k(k_residual<true>, s->res_grid, MEAS_THREADS, meas_smem_bytes<true>(), st, ma);
+      else launch_k(k_residual<false>, s->res_grid, MEAS_THREADS, meas_smem_bytes<false>(), st, ma);
       m->launches++;
     }
     if (overlap) CU(cudaStreamWaitEvent(st, s->ev_join[p], 0));
     {
       ProfScope ps(m, FLB_K_REDUCE);
-      if (md12) k_esikf_post<12><<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid, s->d_scr);
-      else k_esikf_post<6><<<1, dev::ESIKF_THREADS, 0, st>>>(s->ctl, s->partial, s->res_grid, s->d_scr);
+      if (md12) launch_k(k_esikf_post<12>, 1, dev::ESIKF_THREADS, 0, st, s->ctl, (const double*)s->partial, s->res_grid, s->d_scr);
+      else launch_k(k_esikf_post<6>, 1, dev::ESIKF_THREADS, 0, st, s->ctl, (const double*)s->partial, s->res_grid, s->d_scr);
       m->launches++;
     }
   }
@@ -1233,17 +1334,27 @@ static int enqueue_map_incremental(flb_session* s, const double* state26, int fl
   const int n = s->n;
   if (n <= 0 && !from_ctl) return 0;
   const PoseDev pose = from_ctl ? PoseDev{} : pose_from(state26);
-  if (!m->scratch_clean) CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
+  const int npts = from_ctl ? s->cap : n;   // launch geometry / scratch size (the device count is read by the kernels)
+  if (!m->scratch_clean) {
+    // (inside the captured scan sequence these clears sit on the side branch of the first pass)
+    if (!m->capturing && ensure_scratch(m, npts)) return 1;
+    const uint32_t sc0 = next_pow2((uint64_t)std::max(npts, 512) * 2);
+    CU(cudaMemsetAsync(s->d_cnt2, 0, sizeof(int) * 2, st));
+    CU(cudaMemsetAsync(m->skeys, 0xFF, sizeof(uint64_t) * sc0, st));
+    CU(cudaMemsetAsync(m->sbest, 0xFF, sizeof(unsigned long long) * sc0, st));
+  }
+  const uint32_t sc = next_pow2((uint64_t)std::max(npts, 512) * 2);
   {
     ProfScope ps(m, FLB_K_CLASSIFY);
-    k_classify<<<grid_for(from_ctl ? s->cap : n, 256, m->sm_count * 8), 256, 0, st>>>(pose, from_ctl ? s->ctl : nullptr, s->body, s->nbr, s->cnt, n, s->cap,
-                                                                  flg_EKF_inited, s->cfg.filter_size_map_min, s->world, s->cls, s->d_cnt2);
+    launch_k(k_classify, grid_for(npts, 256, m->sm_count * 8), 256, 0, st, pose, (const EsikfCtl*)(from_ctl ? s->ctl : nullptr),
+             (const float4*)s->body, (const float4*)s->nbr, (const unsigned char*)s->cnt, n, s->cap, flg_EKF_inited, s->cfg.filter_size_map_min,
+             s->world, s->cls, s->d_cnt2, m->d, m->skeys, m->sbest, sc - 1);
     m->launches++;
   }
   CU(cudaGetLastError());
   if (from_ctl) {
-    if (insert_device(m, s->world, s->cls, s->cap, 2, &s->ctl->need_host, &s->ctl->n)) return 1;
-  } else if (insert_device(m, s->world, s->cls, n, 2)) return 1;
+    if (insert_device(m, s->world, s->cls, s->cap, 2, &s->ctl->need_host, &s->ctl->n, true)) return 1;
+  } else if (insert_device(m, s->world, s->cls, n, 2, nullptr, nullptr, true)) return 1;
   CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   return 0;
 }
@@ -1363,6 +1474,8 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
   if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
   flb_map* m = s->map;
   if (s->step_pending) return set_err("flb_scan_step_begin: the previous step has not been collected (call flb_scan_step_finish first)");
+  const auto ht0 = std::chrono::steady_clock::now();
+  if (s->host_timing && s->ht_n > 0) s->ht_between += std::chrono::duration<double>(ht0 - s->ht_last_finish).count();
   CU(cudaSetDevice(m->cfg.device));
   s->step_l0 = m->launches;
   s->step_deleted = 0;
@@ -1379,11 +1492,14 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
   s->step_device = s->device_update;
   if (s->step_device) {
     CU(cudaEventRecord(s->ev0, m->stream));
+    const auto hl0 = std::chrono::steady_clock::now();
     if (launch_scan_device(s, state26, P, flg_EKF_inited, true)) return 1;  // :2380 + :2401, no host round trips inside
+    if (s->host_timing) s->ht_launch += std::chrono::duration<double>(std::chrono::steady_clock::now() - hl0).count();
     CU(cudaEventRecord(s->ev1, m->stream));
     CU(cudaEventRecord(s->ev3, m->stream));
   }
   s->step_pending = true;
+  if (s->host_timing) s->ht_begin += std::chrono::duration<double>(std::chrono::steady_clock::now() - ht0).count();
   return 0;
 }
 
@@ -1397,8 +1513,11 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
   memset(&r, 0, sizeof(r));
   r.n_deleted = s->step_deleted;
   bool host_path = !s->step_device;
+  const auto hf0 = std::chrono::steady_clock::now();
+  auto hf1 = hf0;
   if (!host_path) {
     CU(cudaStreamSynchronize(m->stream));                  // the single synchronisation of the step
+    hf1 = std::chrono::steady_clock::now();
     if (finish_counters(m)) return 1;
     m->has_root = m->has_root || m->h_counters[CNT_VALID] > 0;
     if (s->h_ctl->need_host) {
@@ -1429,7 +1548,15 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
   CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
   r.kernel_launches = m->launches - s->step_l0;
   if (out) *out = r;
-  return maybe_rehash(m);
+  const int rrc = maybe_rehash(m);
+  if (s->host_timing) {
+    const auto hf2 = std::chrono::steady_clock::now();
+    s->ht_wait += std::chrono::duration<double>(hf1 - hf0).count();
+    s->ht_finish += std::chrono::duration<double>(hf2 - hf1).count();
+    s->ht_last_finish = hf2;
+    s->ht_n++;
+  }
+  return rrc;
 }
 
 extern "C" int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body, int n, int stride, double* state26, double* P,

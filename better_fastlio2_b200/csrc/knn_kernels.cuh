@@ -19,13 +19,13 @@
 namespace flb {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int BLOCK_RINGS = 3;  // block shells searched by the exact kernel before it falls back to the coarse levels
+constexpr int BLOCK_RINGS = 8;  // block shells searched by the exact kernel (= EXACT_RINGS) before it falls back to the coarse levels
 // exact-kernel launch shape (threads per CTA, minimum CTAs per SM -> register cap)
 #ifndef FLB_KNN_THREADS
 #define FLB_KNN_THREADS 128
 #endif
 #ifndef FLB_KNN_MINB
-#define FLB_KNN_MINB 2
+#define FLB_KNN_MINB 4
 #endif
 constexpr int KNN_THREADS = FLB_KNN_THREADS;
 constexpr int KNN_MIN_CTAS = FLB_KNN_MINB;
@@ -284,92 +284,6 @@ __device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int la
   }
 }
 
-// Scan the blocks flagged in `todo` (bit j: group lane j holds a candidate block: its index `myblk`, occupancy `mymask`
-// and packed block offset `myoff`) with the G lanes of one query group: two blocks per step, group lane gl owns the
-// slots gl, gl+G, ... of each block and keeps up to four independent 16-B point loads in flight.  Voxels inside the
-// 5x5x5 stencil were already visited by the stencil kernel and are masked out when skip_stencil is set.
-template <int K, int G>
-__device__ __forceinline__ void group_scan_blocks(const MapDev& m, unsigned gmask, int gbase, unsigned todo, int myblk,
-                                                  unsigned long long mymask, int myoff, int qbx, int qby, int qbz, int gl, float qx,
-                                                  float qy, float qz, int cvx, int cvy, int cvz, bool skip_stencil, float limit,
-                                                  TopK<K>& t) {
-  static_assert(G == 8 || G == 32, "group width");
-  const unsigned long long lanepat = (G == 32) ? ((1ull << gl) | (1ull << (gl + 32))) : (0x0101010101010101ull << gl);
-  // warp-uniform trip count (the groups of a warp run in lockstep; a group without work idles): divergent groups would
-  // be serialised by the hardware, which multiplies the latency of every query in the warp
-  while (__any_sync(FULL, todo != 0u)) {
-    unsigned long long c0 = 0ull, c1 = 0ull;
-    int b0 = 0, b1 = 0;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int src = todo ? __ffs(todo) - 1 : -1;
-      todo &= todo - 1;   // (0 stays 0)
-      const int sl = gbase + (src >= 0 ? src : 0);
-      const int blk = __shfl_sync(FULL, myblk, sl);
-      const unsigned long long mask = __shfl_sync(FULL, mymask, sl);
-      const int off = __shfl_sync(FULL, myoff, sl);
-      unsigned long long mm = src >= 0 ? (mask & lanepat) : 0ull;
-      if (skip_stencil && mm)
-        mm &= ~block_stencil_mask(qbx + (off & 15) - 8, qby + ((off >> 4) & 15) - 8, qbz + (off >> 8) - 8, cvx, cvy, cvz);
-      if (u == 0) { c0 = mm; b0 = blk; } else { c1 = mm; b1 = blk; }
-    }
-    if constexpr (G == 32) {
-      // a whole warp per query: lane gl owns exactly the slots gl and gl+32 of each block, so the (at most) four
-      // candidates of this step sit at fixed positions — no bit scanning, four independent predicated loads
-      bool ok[4];
-      unsigned pid[4];
-      ok[0] = ((unsigned)c0 >> gl) & 1u; ok[1] = ((unsigned)(c0 >> 32) >> gl) & 1u;
-      ok[2] = ((unsigned)c1 >> gl) & 1u; ok[3] = ((unsigned)(c1 >> 32) >> gl) & 1u;
-      pid[0] = (unsigned)b0 * 64u + (unsigned)gl; pid[1] = pid[0] + 32u;
-      pid[2] = (unsigned)b1 * 64u + (unsigned)gl; pid[3] = pid[2] + 32u;
-      float4 e[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        if (ok[v]) e[v] = __ldg(&m.slots[pid[v]]);
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (ok[v]) {
-          const float4 p = e[v];
-          const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
-          if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
-          walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
-            const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-            if (d2 <= limit) t.insert(d2, o.x, o.y, o.z);
-          });
-        }
-      }
-    } else
-    for (;;) {   // per-lane candidate loop (ordinary SIMT masking: lanes drop out as they run dry)
-      unsigned pid[4];
-      int nc = 0;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        pid[v] = 0u;
-        if (c0) { pid[v] = (unsigned)b0 * 64u + (unsigned)(__ffsll((long long)c0) - 1); c0 &= c0 - 1; nc = v + 1; }
-        else if (c1) { pid[v] = (unsigned)b1 * 64u + (unsigned)(__ffsll((long long)c1) - 1); c1 &= c1 - 1; nc = v + 1; }
-      }
-      if (nc == 0) break;
-      float4 e[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        if (v < nc) e[v] = __ldg(&m.slots[pid[v]]);
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (v < nc) {
-          const float4 p = e[v];
-          const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
-          if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
-          walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
-            const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-            if (d2 <= limit) t.insert(d2, o.x, o.y, o.z);
-          });
-        }
-      }
-      if (nc < 4) break;
-    }
-  }
-}
-
 // Finish ONE query with the whole warp over the coarse levels (rare: map frontier).  A real call (noinline) so that its
 // register needs do not inflate the group kernel; wcount/wthr/seed = state of the query after the block rings (lane r
 // passes result r in sd,sx,sy,sz).
@@ -450,178 +364,263 @@ __device__ __noinline__ void warp_finish_coarse(MapDev m, float4* nbr, unsigned 
 
 // K1b: exact completion of the queries the stencil kernel could not prove complete (its work list).  The stencil
 // kernel has already visited the whole 5x5x5 voxel stencil and left its (up to K) best points in the neighbour cache:
-// they seed the search, which then only looks OUTSIDE the stencil.
-//   * shells of BLOCKS around the query block, radius 1..BLOCK_RINGS, are searched by a GROUP of G lanes per query
-//     (G = 8 for K <= 8: four queries per warp, so a few thousand unresolved queries are all in flight at once — the
-//     kernel is a chain of dependent DRAM/L2 round trips per query, i.e. bound by queries in flight x latency);
-//   * the rare query still unresolved after ring 3 (2.4 m at 0.2 m voxels; map frontier) is finished by the WHOLE warp
-//     over the coarse levels: 3x3x3 coarse cells, then every remaining coarse cell with box-distance pruning.
-template <int K, int G>   // G = lanes per query (group lane r must be able to hold result r: G >= K)
+// they seed the search, which then only looks OUTSIDE the stencil.  One WARP per query, work claimed by atomic tickets.
+//
+// The kernel is a chain of dependent memory round trips per query, so it is built to keep that chain short:
+//   ring r (shell of blocks at Chebyshev block distance r around the query block, r = 1..EXACT_RINGS):
+//     1. the shell positions are enumerated 128 at a time (4 per lane); each is pruned by its box distance against the
+//        current k-th distance, and from ring 3 on by the block-occupancy bitmaps of the 3x3x3 coarse cells around the query
+//        (staged once into shared memory), so that only blocks that exist and can matter are probed;
+//     2. ONE round trip fetches the 32-byte hash entries (block index + voxel occupancy) of all surviving positions;
+//     3. the occupancy words are cut down by the 5^3 stencil (ring 1) and by a separable per-axis slab test against the
+//        k-th distance; the surviving voxels of ALL blocks of the round are compacted into one candidate list in shared
+//        memory (each lane pushes its blocks' voxels at the offset given by a warp prefix sum);
+//     4. the list is consumed 128 candidates at a time: four independent 16-byte point loads per lane and round trip,
+//        then the insertions into lane-local sorted lists;
+//     5. one K-round warp merge per ring gives the new k-th distance and the completeness test
+//        (d_k < distance to the boundary of the searched cube).
+//   Queries still open after ring EXACT_RINGS (nothing within ~6 m at 0.2 m voxels: far outside the map) are finished over
+//   the coarse levels by warp_finish_coarse (remaining blocks of the 3x3x3 coarse cells, then every coarse cell with
+//   box-distance pruning).
+constexpr int EXACT_RINGS = 8;     // rings searched through the 27 staged coarse bitmaps: (q_block +- 8) stays inside them
+constexpr int CAND_CAP = 512;      // per-warp candidate list capacity (voxel slot ids)
+
+struct ExactSmem {
+  unsigned cand[KNN_THREADS / 32][CAND_CAP];
+  unsigned long long cbits[KNN_THREADS / 32][27 * 8];
+};
+
+// shell position idx (0 .. (2r+1)^3 - (2r-1)^3 - 1) of ring r -> block offset; ring 1 enumerates the full 3x3x3 cube instead
+__device__ __forceinline__ void shell_offset(int r, int idx, int& dx, int& dy, int& dz) {
+  const int wd = 2 * r + 1, face = wd * wd;
+  if (idx < 2 * face) {          // the two full slices dz = -r, +r
+    const int sl = idx >= face;
+    const int rem = idx - sl * face;
+    dz = sl ? r : -r;
+    dy = rem / wd - r;
+    dx = rem - (dy + r) * wd - r;
+    return;
+  }
+  const int j = idx - 2 * face, per = 8 * r;
+  const int zi = j / per, p = j - zi * per;
+  dz = zi - (r - 1);
+  if (p < wd) { dx = p - r; dy = -r; }
+  else if (p < 2 * wd) { dx = p - wd - r; dy = r; }
+  else {
+    const int q = p - 2 * wd, side = q / (wd - 2);
+    dy = q - side * (wd - 2) - (r - 1);
+    dx = side ? r : -r;
+  }
+}
+
+// 4-bit mask of the slabs (local voxel coordinate 0..3 along one axis) of block coordinate b that can hold a point
+// within sqrt(bound) of q along this axis (conservative: gaps are shrunk by the rounding margin mg)
+__device__ __forceinline__ unsigned axis_slabs_within(int b, float q, float ds, float mg, float bound) {
+  unsigned m = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float lo = (float)(b * 4 + i) * ds;
+    const float g = fmaxf(fmaxf(lo - q, q - (lo + ds)) - mg, 0.f);
+    m |= (g * g <= bound) ? (1u << i) : 0u;
+  }
+  return m;
+}
+
+template <int K>
 __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
-  static_assert(G >= K && (G == 8 || G == 32), "group width");
-  constexpr int QPW = 32 / G;            // queries per warp
+  pdl_sync();
+  __shared__ ExactSmem sm;
   const MapDev& m = a.m;
-  const int lane = threadIdx.x & 31;
-  const int g = lane / G, gl = lane - g * G, gbase = g * G;
-  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << gbase);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float ds = m.ds;
   const float lim = a.max_d2;
+  unsigned* cand = sm.cand[wid];
+  unsigned long long* cb = sm.cbits[wid];
   FLB_TRACE_BEGIN(3 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !(ctl_pass_active(a.ctl) && a.ctl->converge)) return;
   const int nwork = *a.work_count;
-  // Dynamic distribution: every warp claims the next QPW list entries with one atomic.  Query cost varies by two orders
-  // of magnitude (ring 1 vs ring 3, dense vs empty blocks), so a static stride leaves the kernel waiting for the warp
-  // that happened to draw several expensive queries.
-  for (;;) {
-    int wb = 0;
-    if (lane == 0) wb = atomicAdd(a.work_ticket, QPW);
-    wb = __shfl_sync(FULL, wb, 0);
-    if (wb >= nwork) break;   // warp-uniform
-    const int w = wb + g;
-    const bool active = w < nwork;
-    int i = 0;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
+  // Dynamic distribution: every warp claims the next list entry with one atomic.  Query cost varies by two orders of
+  // magnitude (ring 1 vs far outside the map), so a static stride leaves the kernel waiting for the unlucky warp.
+  // (the first entry of every warp is static — its global warp index — so that a few thousand warps do not start by queueing
+  // on one atomic; only the entries beyond the first wave are claimed by ticket)
+  const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
+  int w = (int)(blockIdx.x * (blockDim.x >> 5)) + wid;
+  for (;; ) {
+    if (w >= nwork) break;   // warp-uniform
+    const int i = a.worklist[w];
+    const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
     TopK<K> t;
     t.clear();
     float rd = CUDART_INF_F, rx = CUDART_NAN_F, ry = CUDART_NAN_F, rz = CUDART_NAN_F, thr = CUDART_INF_F;
-    int gcount = 0;
-    bool done = true;
+    // ---------------- seed: the stencil kernel's result (state as after a merge: lane r holds result r)
+    int gcount = a.cnt[i];
+    if (lane < gcount) {
+      const float4 sd = a.nbr[(size_t)lane * a.stride + i];   // plain load: written by the preceding kernel
+      rd = sd.w; rx = sd.x; ry = sd.y; rz = sd.z;
+      t.d[0] = rd; t.x[0] = rx; t.y[0] = ry; t.z[0] = rz;
+    }
+    {
+      const float dk = __shfl_sync(FULL, rd, K - 1);
+      thr = gcount == K ? dk : CUDART_INF_F;
+    }
+    const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
+    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+    const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+    const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
+    const float bs4 = 4.f * ds;
+    bool done = false;
     FLB_DBG_CLOCK(e0);
     int dbg_rings = 0;
     (void)dbg_rings;
-    int cvx = 0, cvy = 0, cvz = 0;
-    float mg = 0.f;
-    if (active) {
-      i = a.worklist[w];
-      const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
-      qx = q4.x; qy = q4.y; qz = q4.z;
-      // ---------------- seed: the stencil kernel's result (state as after a merge: group lane r holds result r)
-      gcount = a.cnt[i];
-      if (gl < gcount) {
-        const float4 sd = a.nbr[(size_t)gl * a.stride + i];   // plain load: written by the preceding kernel
-        rd = sd.w; rx = sd.x; ry = sd.y; rz = sd.z;
-        t.d[0] = rd; t.x[0] = rx; t.y[0] = ry; t.z[0] = rz;
+#pragma unroll 1
+    for (int r = 1; r <= EXACT_RINGS && !done; ++r) {
+      if (r == 3) {
+        // ---- stage the block-occupancy bitmaps of the 3x3x3 coarse cells around the query (27 x 512 bits)
+        int mycs = -1;
+        if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+          const int wi = lane + 32 * u;
+          const int cs = __shfl_sync(FULL, mycs, min(wi >> 3, 26));
+          if (wi < 27 * 8) cb[wi] = cs >= 0 ? __ldg(&m.cbits[(size_t)cs * 8 + (wi & 7)]) : 0ull;
+        }
+        __syncwarp();
       }
-      done = false;
-      cvx = voxel_of(qx, ds); cvy = voxel_of(qy, ds); cvz = voxel_of(qz, ds);
-      mg = 1e-3f * ds + 4.8e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
-    }
-    {
-      const float dk = __shfl_sync(FULL, rd, gbase + K - 1);
-      thr = gcount == K ? dk : CUDART_INF_F;
-    }
-    const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
-    const float bs4 = 4.f * ds;
-    // ---------------- shells of blocks, radius 1..BLOCK_RINGS.  ALL control flow below is warp-uniform (groups that are
-    // finished idle under predicates): groups on divergent paths would be serialised.  Up to four shell blocks per lane
-    // and round: their hash probes (and then their occupancy words) are independent loads issued back to back.  Ring r
-    // covers >= 4r voxels around the query; ring 3 exceeds the 5 m^2 acceptance radius of h_share_model.
+      const float bound = fminf(gcount == K ? thr : CUDART_INF_F, lim);
+      const int wd = 2 * r + 1;
+      const int nb = (r == 1) ? 27 : wd * wd * wd - (wd - 2) * (wd - 2) * (wd - 2);
 #pragma unroll 1
-    for (int r = 1; r <= BLOCK_RINGS; ++r) {
-      if (!__any_sync(FULL, !done)) break;
-      const bool go = !done;
-      const int wd = 2 * r + 1, nb = wd * wd * wd;
-      // A query that has no k-th distance yet cannot prune anything, and a shell that cuts through a dense surface then
-      // costs hundreds of candidate insertions (the kernel's tail).  Such a query visits the shell in two halves: the
-      // blocks nearer than r block edges first, a merge, then the farther ones — now bounded by the k-th distance just
-      // found, which usually prunes them all before a single probe.
-      const bool need_split = go && gcount < K;
-      const int nhalf = __any_sync(FULL, need_split) ? 2 : 1;    // warp-uniform
-      const float dsplit = need_split ? (float)(r * r) * bs4 * bs4 : CUDART_INF_F;
-#pragma unroll 1
-      for (int half = 0; half < nhalf; ++half) {
-      const float bound = gcount == K ? thr : CUDART_INF_F;
-#pragma unroll 1
-      for (int base = 0; base < nb; base += 4 * G) {
-        int off[4], blk[4];   // off: packed block offsets (dx+8) | (dy+8) << 4 | (dz+8) << 8, -1 = no probe
+      for (int base = 0; base < nb; base += 128) {
+        int blk[4];
         uint4 ent[4];
         unsigned long long mask[4];
+        int bxs[4], bys[4], bzs[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int idx = base + G * u + gl;
-          off[u] = -1;
-          if (go && idx < nb) {
-            const int dx = idx % wd - r, dy = (idx / wd) % wd - r, dz = idx / (wd * wd) - r;
-            // shell only — the interior was visited by smaller rings; ring 1 also takes the query's own block, whose
-            // voxels outside the 5x5x5 stencil have not been seen yet
-            if (r == 1 || max(abs(dx), max(abs(dy), abs(dz))) == r) {
-              const int bx = qbx + dx, by = qby + dy, bz = qbz + dz;
-              const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
-              const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg);
-              if (!(md > bound || md > lim) && (half == 0 ? md <= dsplit : md > dsplit)) {
-                off[u] = (dx + 8) | ((dy + 8) << 4) | ((dz + 8) << 8);
-                const HEntry* he = &m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask];
-                ent[u] = __ldg(reinterpret_cast<const uint4*>(he));
-                mask[u] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));   // same 32-B sector
-              }
+          const int idx = base + 32 * u + lane;
+          blk[u] = -2;   // -2: no probe issued
+          mask[u] = 0ull;
+          if (idx < nb) {
+            int dx, dy, dz;
+            if (r == 1) { dx = idx % 3 - 1; dy = (idx / 3) % 3 - 1; dz = idx / 9 - 1; }   // incl. the query's own block: its
+            else shell_offset(r, idx, dx, dy, dz);                                         // voxels outside the stencil are unseen
+            const int bx = qbx + dx, by = qby + dy, bz = qbz + dz;
+            bxs[u] = bx; bys[u] = by; bzs[u] = bz;
+            const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
+            bool go = !(box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg) > bound);
+            if (go && r >= 3) {
+              const int cell = ((bz >> 3) - (qcz - 1)) * 9 + ((by >> 3) - (qcy - 1)) * 3 + ((bx >> 3) - (qcx - 1));
+              const int bit = ((bz & 7) << 6) | ((by & 7) << 3) | (bx & 7);
+              go = (cb[cell * 8 + (bit >> 6)] >> (bit & 63)) & 1ull;
+            }
+            if (go) {
+              const HEntry* he = &m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask];
+              ent[u] = __ldg(reinterpret_cast<const uint4*>(he));
+              mask[u] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));   // same 32-B sector
+              blk[u] = -1;
             }
           }
         }
+        int c = 0;   // this lane's candidate voxels of the round
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          blk[u] = -1;
-          if (off[u] >= 0) {
-            const uint64_t key = pack_key(qbx + (off[u] & 15) - 8, qby + ((off[u] >> 4) & 15) - 8, qbz + (off[u] >> 8) - 8);
+          if (blk[u] == -1) {
+            const uint64_t key = pack_key(bxs[u], bys[u], bzs[u]);
             const uint64_t k0 = ((uint64_t)ent[u].y << 32) | ent[u].x;
             if (k0 == key) blk[u] = (int)ent[u].z;
             else if (k0 == KEY_EMPTY) { blk[u] = -1; mask[u] = 0ull; }
             else blk[u] = find_block_mask(m, key, mask[u]);   // collision: sequential probe
+            if (blk[u] >= 0 && mask[u]) {
+              if (r == 1) mask[u] &= ~block_stencil_mask(bxs[u], bys[u], bzs[u], cvx, cvy, cvz);
+              if (bound < CUDART_INF_F)
+                mask[u] &= mask_from_axes(axis_slabs_within(bxs[u], qx, ds, mg, bound), axis_slabs_within(bys[u], qy, ds, mg, bound),
+                                          axis_slabs_within(bzs[u], qz, ds, mg, bound));
+            } else mask[u] = 0ull;
           } else mask[u] = 0ull;
+          c += __popcll(mask[u]);
         }
+        // ---- compaction: exclusive prefix of the per-lane candidate counts
+        int incl = c;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const unsigned bal = __ballot_sync(FULL, blk[u] >= 0 && mask[u] != 0ull);
-          const unsigned todo = (G == 32) ? bal : ((bal >> gbase) & ((1u << G) - 1u));
-          group_scan_blocks<K, G>(m, gmask, gbase, todo, blk[u], mask[u], off[u], qbx, qby, qbz, gl, qx, qy, qz, cvx, cvy, cvz,
-                                  r == 1, fminf(lim, bound), t);
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int T = __shfl_sync(FULL, incl, 31);
+        if (T == 0) continue;   // warp-uniform
+        const int mybase = incl - c;
+#pragma unroll 1
+        for (int chunk = 0; chunk < T; chunk += CAND_CAP) {
+          int pos = mybase - chunk;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            unsigned long long mm = mask[u];
+            const unsigned pb = (unsigned)blk[u] * 64u;
+            while (mm) {
+              const int sl = __ffsll((long long)mm) - 1;
+              mm &= mm - 1;
+              if ((unsigned)pos < (unsigned)CAND_CAP) cand[pos] = pb + (unsigned)sl;
+              ++pos;
+            }
+          }
+          __syncwarp();
+          const int n = min(T - chunk, CAND_CAP);
+#pragma unroll 1
+          for (int j0 = 0; j0 < n; j0 += 128) {
+            float4 e[4];
+            bool ok[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const int j = j0 + 32 * v + lane;
+              ok[v] = j < n;
+              if (ok[v]) e[v] = __ldg(&m.slots[cand[j]]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              if (ok[v]) {
+                const float4 p = e[v];
+                const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
+                if (dd <= bound) t.insert(dd, p.x, p.y, p.z);
+                walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
+                  const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+                  if (d2 <= bound) t.insert(d2, o.x, o.y, o.z);
+                });
+              }
+            }
+          }
+          __syncwarp();
         }
       }
-      if (half + 1 < nhalf) {   // intermediate merge: gives the far half its bound
-        const int gc = warp_merge<K>(t, gmask, gl, lane, rd, rx, ry, rz, thr);
-        if (go) gcount = gc;
-      }
-      }
-      {
-        // merge (all groups together; for a finished group it reproduces its result)
-        const int gc = warp_merge<K>(t, gmask, gl, lane, rd, rx, ry, rz, thr);
-        if (go) {
-          gcount = gc;
-          dbg_rings = r;
-          const float cov = cover2(qx, qy, qz, (float)(qbx - r) * bs4, (float)(qby - r) * bs4, (float)(qbz - r) * bs4,
-                                   (float)(qbx + r + 1) * bs4, (float)(qby + r + 1) * bs4, (float)(qbz + r + 1) * bs4, mg);
-          done = (gcount == K && thr < cov) || cov > lim;
-        }
-      }
+      // ---- merge the lane-local lists: new k-th distance, completeness of the searched cube
+      gcount = warp_merge<K>(t, FULL, lane, lane, rd, rx, ry, rz, thr);
+      dbg_rings = r;
+      const float cov = cover2(qx, qy, qz, (float)(qbx - r) * bs4, (float)(qby - r) * bs4, (float)(qbz - r) * bs4,
+                               (float)(qbx + r + 1) * bs4, (float)(qby + r + 1) * bs4, (float)(qbz + r + 1) * bs4, mg);
+      done = (gcount == K && thr < cov) || cov > lim;
     }
-    if (active && done) {
-      if (gl < K) a.nbr[(size_t)gl * a.stride + i] = make_float4(rx, ry, rz, rd);
-      if (gl == 0) {
+    if (done) {
+      if (lane < K) a.nbr[(size_t)lane * a.stride + i] = make_float4(rx, ry, rz, rd);
+      if (lane == 0) {
         a.cnt[i] = (unsigned char)gcount;
         if (a.phase_stats) atomicAdd(&a.phase_stats[1], 1);
       }
     }
 #ifdef FLB_TRACE
-    if (active && gl == 0 && a.ctl && a.ctl->it == -1) {
+    if (lane == 0 && a.ctl && a.ctl->it == -1) {
       const long long e1 = clock64();
-      FLB_DBG_ADD(16, 1); FLB_DBG_ADD(17, e1 - e0); FLB_DBG_MAX(18, e1 - e0); FLB_DBG_ADD(18 + dbg_rings, 1);
+      FLB_DBG_ADD(16, 1); FLB_DBG_ADD(17, e1 - e0); FLB_DBG_MAX(18, e1 - e0); FLB_DBG_ADD(18 + min(dbg_rings, 6), 1);
       FLB_DBG_ADD(25, done ? 0 : 1);
     }
 #endif
-    // ---------------- queries still unresolved after the block rings: the WHOLE warp finishes them one at a time over
-    // the coarse levels (the blocks of the rings are skipped inside scan_coarse_cell)
-    __syncwarp();
-    unsigned pend = __ballot_sync(FULL, active && !done && gl == 0);
-    while (pend) {
-      const int src = __ffs(pend) - 1;   // leader lane of the unresolved group
-      pend &= pend - 1;
-      const int qi = __shfl_sync(FULL, i, src);
-      const float wqx = __shfl_sync(FULL, qx, src), wqy = __shfl_sync(FULL, qy, src), wqz = __shfl_sync(FULL, qz, src);
-      int wcount = __shfl_sync(FULL, gcount, src);
-      float wthr = __shfl_sync(FULL, thr, src);
-      const int sl = src + (lane < K ? lane : 0);   // result r of that query lives in its group lane r
-      const float sd = __shfl_sync(FULL, rd, sl), sx = __shfl_sync(FULL, rx, sl), sy = __shfl_sync(FULL, ry, sl), sz = __shfl_sync(FULL, rz, sl);
-      warp_finish_coarse<K>(m, a.nbr, a.cnt, a.phase_stats, a.stride, lim, qi, wqx, wqy, wqz, wcount, wthr, sd, sx, sy, sz);
+    // ---------------- still unresolved after the block rings: finish over the coarse levels (the blocks of the rings
+    // are skipped inside scan_coarse_cell)
+    if (!done) {
+      __syncwarp();
+      warp_finish_coarse<K>(m, a.nbr, a.cnt, a.phase_stats, a.stride, lim, i, qx, qy, qz, gcount, thr, rd, rx, ry, rz);
     }
+    if (lane == 0) w = nwarps + atomicAdd(a.work_ticket, 1);
+    w = __shfl_sync(FULL, w, 0);
   }
   FLB_TRACE_END(3 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
 }
@@ -718,12 +717,12 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const StencilSmem&
     for (int u = 0; u < 4; ++u) {
       if (u < nc) {
         float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
-        if (dd <= lim) t.insert(dd, pid[u]);
+        if (dd <= lim && dd < t.d[K - 1]) t.insert(dd, pid[u]);   // (the guard lets a warp skip the insertion network when no lane needs it)
         ++n_head;
         walk_chain(m, __float_as_int(e[u].w), [&](const float4 o, int c) {  // overflow chain of this voxel
           ++n_chain;
           const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-          if (d2 <= lim) t.insert(d2, 0x80000000u | (unsigned)c);
+          if (d2 <= lim && d2 < t.d[K - 1]) t.insert(d2, 0x80000000u | (unsigned)c);
         });
       }
     }
@@ -731,22 +730,34 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const StencilSmem&
   }
 }
 
-// Outer-shell pass: (1) a flat, load-free loop tests every occupied shell voxel against the k-th distance known after
-// the inner pass (box lower bound from the per-axis gap tables) and compacts the survivors into a small per-thread list
-// — lanes only diverge on cheap code; (2) the survivors are loaded four at a time.  Returns false if the list overflowed
-// (the caller then visits the whole shell).
+// Outer-shell pass (the 98 voxels of the 5x5x5 stencil outside the inner 3x3x3).  After the inner pass the k-th distance is
+// usually far smaller than the stencil, so the shell is cut down BEFORE any per-voxel work: per axis, the 5 slabs whose gap
+// to the query exceeds the k-th distance are dropped (15 compares), the three 5-bit slab masks are expanded to the 8
+// blocks with the separable mask builder, and only the occupied voxels inside that box go through (1) a flat, load-free
+// loop that applies the exact box lower bound (sum of the three gaps) and compacts the survivors into a small per-thread
+// list — lanes only diverge on cheap code — and (2) the loads, four survivors at a time.  Returns false if the list
+// overflowed (no k-th distance yet, sparse surroundings: the caller then visits the whole shell).
+// (ncu source view, round 1: walking all ~60 occupied shell voxels per query one by one was 30 % of the kernel's instructions.)
 template <int K>
-__device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem& sm, int tid, unsigned ix, unsigned iy, unsigned iz,
-                                                   int ox, int oy, int oz, float qx, float qy, float qz, float lim,
-                                                   TopKId<K>& t, int& n_head, int& n_chain) {
+__device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem& sm, int tid, int ox, int oy, int oz, float qx,
+                                                   float qy, float qz, float lim, TopKId<K>& t, int& n_head, int& n_chain) {
   const float bound = t.d[K - 1];
+  if (!(bound < CUDART_INF_F)) return false;   // nothing to prune with
+  unsigned wx = 0u, wy = 0u, wz = 0u;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    wx |= (sm.gap[j][tid] <= bound) ? (1u << j) : 0u;
+    wy |= (sm.gap[5 + j][tid] <= bound) ? (1u << j) : 0u;
+    wz |= (sm.gap[10 + j][tid] <= bound) ? (1u << j) : 0u;
+  }
+  const unsigned ax = wx << ox, ay = wy << oy, az = wz << oz;   // 8-bit masks over the two blocks per axis
   int ns = 0;
-  {
-    int b = -1;
-    unsigned long long cand = 0ull;
-    for (;;) {
-      while (cand == 0ull && b < 7) { ++b; cand = sm.c5[b][tid] & ~inner_mask(sm, tid, b); }
-      if (cand == 0ull) break;
+#pragma unroll 1
+  for (int b = 0; b < 8; ++b) {
+    unsigned long long cand = sm.c5[b][tid] & stencil_mask(ax, ay, az, b);
+    if (cand == 0ull) continue;
+    cand &= ~inner_mask(sm, tid, b);
+    while (cand != 0ull) {
       const int sl = __ffsll((long long)cand) - 1;
       cand &= cand - 1;
       // stencil-relative voxel index per axis (0..4): block half * 4 + local coordinate - stencil origin
@@ -758,7 +769,7 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem&
       }
     }
   }
-  if (ns > SHELL_LIST) return false;  // (sparse inner region: hardly anything could be pruned)
+  if (ns > SHELL_LIST) return false;
   for (int base = 0; base < ns; base += 4) {
     unsigned pid[4];
     float4 e[4];
@@ -778,12 +789,12 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem&
     for (int u = 0; u < 4; ++u) {
       if (base + u < ns) {
         float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
-        if (dd <= lim) t.insert(dd, pid[u]);
+        if (dd <= lim && dd < t.d[K - 1]) t.insert(dd, pid[u]);
         ++n_head;
         walk_chain(m, __float_as_int(e[u].w), [&](const float4 o, int c) {  // overflow chain of this voxel
           ++n_chain;
           const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-          if (d2 <= lim) t.insert(d2, 0x80000000u | (unsigned)c);
+          if (d2 <= lim && d2 < t.d[K - 1]) t.insert(d2, 0x80000000u | (unsigned)c);
         });
       }
     }
@@ -793,6 +804,7 @@ __device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem&
 
 template <int K>
 __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
+  pdl_sync();
   __shared__ StencilSmem sm;
   const MapDev& m = a.m;
   const int tid = threadIdx.x;
@@ -862,8 +874,8 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
     stencil_pass<K, false>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);
-    if (!stencil_shell_pass<K>(m, sm, tid, ix, iy, iz, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain))
-      stencil_pass<K, true>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);  // list overflow: visit the whole shell
+    if (!stencil_shell_pass<K>(m, sm, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain))
+      stencil_pass<K, true>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);  // no bound / list overflow: the whole shell
     if (a.phase_stats) {  // profiling only: candidate statistics
       atomicAdd(&a.phase_stats[4], n_chain);
       atomicMax(&a.phase_stats[5], n_chain);

@@ -117,6 +117,7 @@ __device__ __forceinline__ void touch_block(const MapDev& m, uint64_t key, int b
 // cls == nullptr: every point; else only points whose class has its bit in cls_mask (bit1: ToAdd, bit2: NoNeed).
 __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
                                int cls_mask, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  pdl_sync();
   FLB_TRACE_BEGIN(7 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
@@ -134,6 +135,7 @@ __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const u
 // Add_Points(..., downsample_on=false) (ikd_Tree.cpp:471-472) and Build (ikd_Tree.cpp:352-364): no dedupe.
 __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
                                 int want_cls, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  pdl_sync();
   FLB_TRACE_BEGIN(10 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
@@ -153,11 +155,13 @@ __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const 
       // owner of the head slot: write xyz only — w (= -1 by invariant) may concurrently receive a chain push
       float* f = reinterpret_cast<float*>(&m.slots[idx]);
       f[0] = p.x; f[1] = p.y; f[2] = p.z;
+      m.sint[idx] = p.w;
     } else {
       const int node = alloc_ovf(m);
       if (node < 0) continue;
       const int prev = atomicExch(reinterpret_cast<int*>(&m.slots[idx]) + 3, node);
       m.ovf[node] = make_float4(p.x, p.y, p.z, __int_as_float(prev));
+      m.oint[node] = p.w;
     }
     atomicAdd(&m.counters[CNT_VALID], 1);
   }
@@ -173,6 +177,7 @@ __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const 
 // Only bump allocation and free-stack pushes happen here (no pops), as the allocator contract requires.
 __global__ void k_relocate_chains(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int want_cls,
                                   int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  pdl_sync();
   FLB_TRACE_BEGIN(11 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
@@ -204,6 +209,7 @@ __global__ void k_relocate_chains(MapDev m, const float4* __restrict__ pts, cons
         for (int j = 0; j < L; ++j) {
           const float4 e = __ldcg(&m.ovf[c]);
           m.ovf[base + j] = make_float4(e.x, e.y, e.z, __int_as_float(j + 1 < L ? base + j + 1 : -1));
+          m.oint[base + j] = __ldcg(&m.oint[c]);
           free_ovf_node(m, c);
           c = __float_as_int(e.w);
         }
@@ -244,9 +250,25 @@ __device__ __forceinline__ float dist_pt_to_centre_of(const float4 e, const floa
 
 // Scratch hash: per voxel touched by this batch, the best NEW point = min (dist to centre, later index wins ties —
 // the reference processes points in order and a later point replaces an equal-distance earlier one, :436-447).
+__device__ __forceinline__ void ds_scatter_one(const MapDev& m, const float4 p, int i, uint64_t vkey, uint64_t* skeys,
+                                               unsigned long long* sbest, uint32_t smask) {
+  const float d = dist_to_voxel_centre(p, m.ds);
+  const unsigned long long pk = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+  uint32_t s = hash_key(vkey) & smask;
+  for (uint32_t probe = 0; probe <= smask; ++probe) {
+    uint64_t k = *((volatile uint64_t*)&skeys[s]);
+    if (k == KEY_EMPTY) {
+      uint64_t old = atomicCAS((unsigned long long*)&skeys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)vkey);
+      if (old == KEY_EMPTY || old == vkey) k = vkey;
+    }
+    if (k == vkey) { atomicMin(&sbest[s], pk); break; }
+    s = (s + 1) & smask;
+  }
+}
 __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int n,
                              uint64_t* skeys, unsigned long long* sbest, uint32_t smask, const int* __restrict__ skip,
                              const int* __restrict__ n_dev) {
+  pdl_sync();
   FLB_TRACE_BEGIN(8 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
@@ -254,19 +276,7 @@ __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const uns
     if (cls && cls[i] != 1) continue;
     const float4 p = pts[i];
     if (!coord_ok(p.x, p.y, p.z, m.ds)) continue;
-    const uint64_t vkey = pack_key(voxel_of(p.x, m.ds), voxel_of(p.y, m.ds), voxel_of(p.z, m.ds));
-    const float d = dist_to_voxel_centre(p, m.ds);
-    const unsigned long long pk = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
-    uint32_t s = hash_key(vkey) & smask;
-    for (uint32_t probe = 0; probe <= smask; ++probe) {
-      uint64_t k = *((volatile uint64_t*)&skeys[s]);
-      if (k == KEY_EMPTY) {
-        uint64_t old = atomicCAS((unsigned long long*)&skeys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)vkey);
-        if (old == KEY_EMPTY || old == vkey) k = vkey;
-      }
-      if (k == vkey) { atomicMin(&sbest[s], pk); break; }
-      s = (s + 1) & smask;
-    }
+    ds_scatter_one(m, p, i, pack_key(voxel_of(p.x, m.ds), voxel_of(p.y, m.ds), voxel_of(p.z, m.ds)), skeys, sbest, smask);
   }
   FLB_TRACE_END(8 * 8);
 }
@@ -279,6 +289,7 @@ __global__ void k_ds_scatter(MapDev m, const float4* __restrict__ pts, const uns
 __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls, int n,
                            const uint64_t* __restrict__ skeys, const unsigned long long* __restrict__ sbest,
                            uint32_t smask, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+  pdl_sync();
   FLB_TRACE_BEGIN(9 * 8);
   if (skip && *skip) return;
   if (n_dev) n = *n_dev;
@@ -309,6 +320,7 @@ __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsig
     if (!(mask & bit)) {
       float* f = reinterpret_cast<float*>(&m.slots[idx]);
       f[0] = p.x; f[1] = p.y; f[2] = p.z;  // w stays -1
+      m.sint[idx] = p.w;
       atomicOr((unsigned long long*)&m.hent[hs].mask, bit);
       atomicAdd(&m.counters[CNT_VALID], 1);
       atomicAdd(&m.counters[CNT_SCRATCH0], 1);
@@ -319,15 +331,16 @@ __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsig
     int L = 1;
     float bestd = d;
     float4 best = p;
+    float besti = p.w;
     bool new_wins = true;
     {
       float de = dist_pt_to_centre_of(head, p, m.ds);
-      if (de < bestd) { bestd = de; best = head; new_wins = false; }
+      if (de < bestd) { bestd = de; best = head; besti = m.sint[idx]; new_wins = false; }
     }
     for (int c = __float_as_int(head.w); c >= 0;) {
       const float4 e = m.ovf[c];
       float de = dist_pt_to_centre_of(e, p, m.ds);
-      if (de < bestd) { bestd = de; best = e; new_wins = false; }
+      if (de < bestd) { bestd = de; best = e; besti = m.oint[c]; new_wins = false; }
       ++L;
       c = __float_as_int(e.w);
     }
@@ -339,6 +352,7 @@ __global__ void k_ds_apply(MapDev m, const float4* __restrict__ pts, const unsig
         c = nx;
       }
       m.slots[idx] = make_float4(best.x, best.y, best.z, __int_as_float(-1));
+      m.sint[idx] = besti;
       if (L != 1) atomicAdd(&m.counters[CNT_VALID], 1 - L);
       atomicAdd(&m.counters[CNT_SCRATCH0], 1);
     }
@@ -427,7 +441,7 @@ __global__ void k_delete(MapDev m, const float* __restrict__ params, int np, int
       if (hit(head)) {
         ++ndel;
         const int c = __float_as_int(head.w);
-        if (c >= 0) { m.slots[idx] = m.ovf[c]; free_ovf_node(m, c); }
+        if (c >= 0) { m.slots[idx] = m.ovf[c]; m.sint[idx] = m.oint[c]; free_ovf_node(m, c); }
         else clear |= 1ull << s;  // w already -1
       }
     }
@@ -488,14 +502,16 @@ __global__ void k_collect(MapDev m, int nblk, int mode, const float* __restrict_
       const int s = lane + 32 * h;
       if (!((mask >> s) & 1ull)) continue;
       float4 e = m.slots[(size_t)b * 64 + s];
+      float inten = m.sint[(size_t)b * 64 + s];
       for (;;) {
         if (pass(e)) {
-          if (out && w < cap) out[w] = make_float4(e.x, e.y, e.z, 0.f);
+          if (out && w < cap) out[w] = make_float4(e.x, e.y, e.z, inten);
           ++w;
         }
         const int c = __float_as_int(e.w);
         if (c < 0) break;
         e = m.ovf[c];
+        inten = m.oint[c];
       }
     }
   }
@@ -554,11 +570,37 @@ __global__ void k_rehash_insert(MapDev m, int nblk) {
   }
 }
 
-// strided host points -> float4
-__global__ void k_pack_points(const unsigned char* __restrict__ src, int stride, float4* dst, int n) {
+// strided host points -> float4 (x, y, z, intensity); off_i < 0: no intensity in the records (0)
+__global__ void k_pack_points(const unsigned char* __restrict__ src, int stride, int off_i, float4* dst, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
-    dst[i] = make_float4(p[0], p[1], p[2], 0.f);
+    const float w = off_i >= 0 ? *reinterpret_cast<const float*>(src + (size_t)i * stride + off_i) : 0.f;
+    dst[i] = make_float4(p[0], p[1], p[2], w);
+  }
+}
+// intensity of returned neighbours (API searches only; off the hot path): the neighbour's voxel is re-read and the point with
+// exactly these coordinates looked up.  pts: (x, y, z, d2) records, NaN x = no neighbour.
+__global__ void k_lookup_intensity(MapDev m, const float4* __restrict__ pts, float* __restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    float r = 0.f;
+    if (p.x == p.x && coord_ok(p.x, p.y, p.z, m.ds)) {
+      const int vx = voxel_of(p.x, m.ds), vy = voxel_of(p.y, m.ds), vz = voxel_of(p.z, m.ds);
+      const int blk = find_block(m, pack_key(vx >> 2, vy >> 2, vz >> 2));
+      if (blk >= 0) {
+        const size_t idx = (size_t)blk * 64 + ((((vz & 3) << 2) + (vy & 3)) * 4 + (vx & 3));
+        float4 e = m.slots[idx];
+        float inten = m.sint[idx];
+        for (;;) {
+          if (e.x == p.x && e.y == p.y && e.z == p.z) { r = inten; break; }
+          const int c = __float_as_int(e.w);
+          if (c < 0) break;
+          e = m.ovf[c];
+          inten = m.oint[c];
+        }
+      }
+    }
+    out[i] = r;
   }
 }
 

@@ -5,6 +5,7 @@
 // contraction: this TU is compiled with -fmad=false), Jacobian rows and the normal equations in double.
 #pragma once
 #include "knn_kernels.cuh"
+#include "map_kernels.cuh"
 
 namespace flb {
 
@@ -258,6 +259,7 @@ constexpr int meas_smem_bytes() { return (MEAS_THREADS / 32) * 32 * (EXTR ? 13 :
 
 template <bool EXTR>
 __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
+  pdl_sync();
   constexpr int W = EXTR ? 13 : 7;               // augmented row width [cols..., h]
   constexpr int NE = W * (W + 1) / 2;            // 91 or 28
   constexpr int EPL = (NE + 31) / 32;            // entries per lane
@@ -392,9 +394,14 @@ __global__ void k_sel_to_int(const unsigned char* __restrict__ sel, int* __restr
 // ---------------------------------------------------------------------------------------------- map_incremental classifier
 // laserMapping.cpp:1440-1490. cls: 0 dropped, 1 PointToAdd (downsample), 2 PointNoNeedDownsample.
 // counts[0] += #ToAdd, counts[1] += #NoNeed.
+// Fused with the first two steps of the insert (K3a touch_block: make sure the block of every point to be added exists;
+// K3c scatter: per-voxel best new point of the downsampled class into the scratch hash) when a scratch hash is passed:
+// both only need the point and its class, so the points are read once and two launches disappear from the scan's tail.
 __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __restrict__ body, const float4* __restrict__ nbr,
                            const unsigned char* __restrict__ cnt, int n_in, int nbr_stride, int flg_in, double fs,
-                           float4* __restrict__ world, unsigned char* __restrict__ cls, int* counts) {
+                           float4* __restrict__ world, unsigned char* __restrict__ cls, int* counts, MapDev m, uint64_t* skeys,
+                           unsigned long long* sbest, uint32_t smask) {
+  pdl_sync();
   FLB_TRACE_BEGIN(6 * 8);
   if (ctl && ctl->need_host) return;  // the host fallback redoes update + insert for this scan
   const PoseDev s = ctl ? ctl->pose : s_in;
@@ -434,6 +441,14 @@ __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __re
         c = 1;
       }
       cls[i] = (unsigned char)c;
+      if (skeys && c != 0) {
+        if (!coord_ok(pw.x, pw.y, pw.z, m.ds)) atomicOr(&m.counters[CNT_ERROR], ERR_RANGE);
+        else {
+          const int vx = voxel_of(pw.x, m.ds), vy = voxel_of(pw.y, m.ds), vz = voxel_of(pw.z, m.ds);
+          touch_block(m, pack_key(vx >> 2, vy >> 2, vz >> 2), vx >> 2, vy >> 2, vz >> 2);
+          if (c == 1) ds_scatter_one(m, pw, i, pack_key(vx, vy, vz), skeys, sbest, smask);
+        }
+      }
     }
     const unsigned b1 = __ballot_sync(FULL, c == 1), b2 = __ballot_sync(FULL, c == 2);
     if (lane == 0) {

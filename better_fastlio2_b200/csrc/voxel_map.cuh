@@ -13,6 +13,9 @@
 //   bslot[B]          hash slot of each allocated block (for the kernels that iterate blocks densely)
 //   slots[B*64]       float4 head point of each voxel: x,y,z and w = int index of an overflow node (-1: none).
 //                     INVARIANT: w == -1 whenever the voxel has no overflow chain (also while the voxel is empty).
+//   sint[B*64], oint[O]  intensity of the head point of each voxel / of each overflow node (the reference tree stores whole
+//                     PointType records, ikd_Tree.h:64-86; FAST-LIO map points carry x,y,z,intensity — normals and curvature are
+//                     zero, laserMapping.cpp:1101-1110).  Side arrays: the k-NN hot path never touches them.
 //   ovf[O]            float4 overflow nodes (x,y,z, w = next) for the rare voxels holding > 1 point
 //                     (first Build, no-downsample inserts: SURVEY.md §3.3).  A linked list per voxel; after every
 //                     verbatim insert the chains it touched are re-laid CONTIGUOUSLY (k_relocate_chains: next == this + 1),
@@ -26,6 +29,16 @@
 #include "trace.cuh"
 
 namespace flb {
+
+// Programmatic dependent launch (sm_90+): the kernels of a scan are launched with the programmatic-stream-serialization
+// attribute, so a kernel's launch (grid setup, CTA scheduling, parameter fetch) overlaps the tail of its predecessor in
+// the stream / graph instead of starting only after it has drained.  Every such kernel calls this first: it blocks
+// until ALL prerequisite grids have completed and their memory is visible (so nothing below it can see stale data), and
+// then allows its own dependents to be scheduled.  A no-op for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t KEY_TOMB = 0xFFFFFFFFFFFFFFFEull;
@@ -64,7 +77,9 @@ struct MapDev {
   HEntry* hent;
   uint32_t* bslot;
   float4* slots;
+  float* sint;
   float4* ovf;
+  float* oint;
   uint64_t* bkey;
   uint64_t* brel;        // per-block scratch bitmap of k_relocate_chains (all zero between kernels)
   uint32_t* free_blk;

@@ -71,6 +71,14 @@ int flb_map_reconstruct(flb_map* m, const float* xyz, int n, int stride_bytes);
  * (the reference returns the number of sequential add operations, which its caller overwrites without reading,
  * laserMapping.cpp:1492-1494; the two differ only when several new points fall into one voxel). */
 int flb_map_add_points(flb_map* m, const float* xyz, int n, int stride_bytes, int downsample_on, int* n_added);
+/* PointType-aware variants.  The reference tree stores whole pcl::PointXYZINormal records (ikd_Tree.h:64-86) and hands them
+ * back from Nearest_Search / flatten (featsFromMap for publishing and saving, laserMapping.cpp:2361-2367); FAST-LIO map
+ * points carry x, y, z, intensity (normals and curvature are zero, laserMapping.cpp:1101-1110).  These entry points read the
+ * intensity at off_intensity bytes into each record (< 0: none -> 0) and keep it with the map point; the plain xyz entry
+ * points above store intensity 0, except that 16-byte records are always taken as (x, y, z, intensity). */
+int flb_map_build_pt(flb_map* m, const void* pts, int n, int stride_bytes, int off_intensity);
+int flb_map_reconstruct_pt(flb_map* m, const void* pts, int n, int stride_bytes, int off_intensity);
+int flb_map_add_points_pt(flb_map* m, const void* pts, int n, int stride_bytes, int off_intensity, int downsample_on, int* n_added);
 /* Delete_Point_Boxes (ikd_Tree.cpp:535-556): boxes = nb x {min xyz, max xyz} (BoxPointType, ikd_Tree.h:32-35),
  * half-open test min <= p < max (ikd_Tree.cpp:670); *n_deleted = number of points removed. */
 int flb_map_delete_boxes(flb_map* m, const float* boxes6, int nb, int* n_deleted);
@@ -85,10 +93,16 @@ int flb_map_nearest_search(flb_map* m, const float* q_xyz, int nq, int stride_by
  * Writes up to cap points; *n_found is the total. */
 int flb_map_box_search(flb_map* m, const float* box6, float* out_xyz, int cap, int* n_found);
 int flb_map_radius_search(flb_map* m, const float* center_xyz, float radius, float* out_xyz, int cap, int* n_found);
+/* the same searches returning (x, y, z, intensity) records: out_xyzi[nq*k*4] resp. out_xyzi[cap*4] */
+int flb_map_nearest_search_xyzi(flb_map* m, const float* q_xyz, int nq, int stride_bytes, int k, float max_dist,
+                                float* out_xyzi, float* out_d2, int* out_cnt);
+int flb_map_box_search_xyzi(flb_map* m, const float* box6, float* out_xyzi, int cap, int* n_found);
+int flb_map_radius_search_xyzi(flb_map* m, const float* center_xyz, float radius, float* out_xyzi, int cap, int* n_found);
 int flb_map_validnum(flb_map* m);  /* validnum(), ikd_Tree.cpp:128-145 ; -1 on error */
 int flb_map_size(flb_map* m);      /* size(), ikd_Tree.cpp:78-96 (== validnum here: no lazy tombstones) */
 /* flatten (ikd_Tree.cpp:1325-1352): all valid points, arbitrary order. Writes up to cap; *n = total valid. */
 int flb_map_flatten(flb_map* m, float* out_xyz, int cap, int* n);
+int flb_map_flatten_xyzi(flb_map* m, float* out_xyzi, int cap, int* n);   /* (x, y, z, intensity) records */
 /* tree_range (ikd_Tree.h:245): bounding box of valid points {min xyz, max xyz}. */
 int flb_map_range(flb_map* m, float* box6);
 
@@ -132,6 +146,9 @@ void flb_session_destroy(flb_session* s);
 /* feats_down_body (laserMapping.cpp:2322-2325): upload the voxel-downsampled, undistorted scan (LiDAR frame).
  * Resets the per-scan caches (Nearest_Points, point_selected_surf := true, laserMapping.cpp:2131). */
 int flb_scan_upload(flb_session* s, const float* body_xyz, int n, int stride_bytes);
+/* same for PointType records: the intensity at off_intensity (< 0: none) travels with the point into the map, as
+ * pointBodyToWorld copies it (laserMapping.cpp:1101-1110).  16-byte records are (x, y, z, intensity). */
+int flb_scan_upload_pt(flb_session* s, const void* body_pts, int n, int stride_bytes, int off_intensity);
 /* Asynchronous variant for streaming callers: starts the host->device copy of the NEXT scan on a copy stream into a
  * second buffer and returns immediately, so the transfer overlaps the processing of the current scan.  The scan
  * becomes current at the next flb_scan_step / flb_esikf_update called with body == NULL (which waits for the copy).

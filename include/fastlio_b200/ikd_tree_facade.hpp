@@ -13,6 +13,7 @@
 #pragma once
 #include <pcl/point_types.h>  // same include as ikd_Tree.h:11 (point structs + Eigen::aligned_allocator)
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -57,12 +58,12 @@ class KD_TREE {
 
   void Build(PointVector point_cloud) {
     if (!ensure()) return;
-    if (flb_map_build(map_, xyz(point_cloud), (int)point_cloud.size(), (int)sizeof(PointType))) report("Build");
+    if (flb_map_build_pt(map_, xyz(point_cloud), (int)point_cloud.size(), (int)sizeof(PointType), off_intensity())) report("Build");
     sync_root();
   }
   void reconstruct(PointVector point_cloud) {
     if (!ensure()) return;
-    if (flb_map_reconstruct(map_, xyz(point_cloud), (int)point_cloud.size(), (int)sizeof(PointType))) report("reconstruct");
+    if (flb_map_reconstruct_pt(map_, xyz(point_cloud), (int)point_cloud.size(), (int)sizeof(PointType), off_intensity())) report("reconstruct");
     sync_root();
   }
 
@@ -71,10 +72,10 @@ class KD_TREE {
     PointVector().swap(Nearest_Points);
     std::vector<float>().swap(Point_Distance);
     if (!map_ || k_nearest < 1) return;
-    std::vector<float> oxyz((size_t)k_nearest * 3), od2(k_nearest);
+    std::vector<float> oxyz((size_t)k_nearest * 4), od2(k_nearest);
     int cnt = 0;
     const float md = std::isfinite(max_dist) ? (float)max_dist : 0.f;
-    if (flb_map_nearest_search(map_, &point.x, 1, (int)sizeof(PointType), k_nearest, md, oxyz.data(), od2.data(), &cnt)) {
+    if (flb_map_nearest_search_xyzi(map_, &point.x, 1, (int)sizeof(PointType), k_nearest, md, oxyz.data(), od2.data(), &cnt)) {
       report("Nearest_Search");
       return;
     }
@@ -102,18 +103,18 @@ class KD_TREE {
     const float b[6] = {Box_of_Point.vertex_min[0], Box_of_Point.vertex_min[1], Box_of_Point.vertex_min[2],
                         Box_of_Point.vertex_max[0], Box_of_Point.vertex_max[1], Box_of_Point.vertex_max[2]};
     int n = 0;
-    if (flb_map_box_search(map_, b, nullptr, 0, &n)) { report("Box_Search"); return; }
-    std::vector<float> o((size_t)std::max(n, 1) * 3);
-    if (flb_map_box_search(map_, b, o.data(), n, &n)) { report("Box_Search"); return; }
+    if (flb_map_box_search_xyzi(map_, b, nullptr, 0, &n)) { report("Box_Search"); return; }
+    std::vector<float> o((size_t)std::max(n, 1) * 4);
+    if (flb_map_box_search_xyzi(map_, b, o.data(), n, &n)) { report("Box_Search"); return; }
     fill(Storage, o.data(), n);
   }
   void Radius_Search(PointType point, const float radius, PointVector& Storage) {
     Storage.clear();
     if (!map_) return;
     int n = 0;
-    if (flb_map_radius_search(map_, &point.x, radius, nullptr, 0, &n)) { report("Radius_Search"); return; }
-    std::vector<float> o((size_t)std::max(n, 1) * 3);
-    if (flb_map_radius_search(map_, &point.x, radius, o.data(), n, &n)) { report("Radius_Search"); return; }
+    if (flb_map_radius_search_xyzi(map_, &point.x, radius, nullptr, 0, &n)) { report("Radius_Search"); return; }
+    std::vector<float> o((size_t)std::max(n, 1) * 4);
+    if (flb_map_radius_search_xyzi(map_, &point.x, radius, o.data(), n, &n)) { report("Radius_Search"); return; }
     fill(Storage, o.data(), n);
   }
 
@@ -121,7 +122,7 @@ class KD_TREE {
     if (PointToAdd.empty()) return 0;
     if (!ensure()) return 0;
     int added = 0;
-    if (flb_map_add_points(map_, xyz(PointToAdd), (int)PointToAdd.size(), (int)sizeof(PointType), downsample_on ? 1 : 0, &added)) report("Add_Points");
+    if (flb_map_add_points_pt(map_, xyz(PointToAdd), (int)PointToAdd.size(), (int)sizeof(PointType), off_intensity(), downsample_on ? 1 : 0, &added)) report("Add_Points");
     sync_root();
     return added;
   }
@@ -141,12 +142,12 @@ class KD_TREE {
   void flatten(KD_TREE_NODE* root, PointVector& Storage, delete_point_storage_set) {
     if (!root || !map_) return;
     int n = 0;
-    if (flb_map_flatten(map_, nullptr, 0, &n)) { report("flatten"); return; }
-    std::vector<float> o((size_t)std::max(n, 1) * 3);
-    if (flb_map_flatten(map_, o.data(), n, &n)) { report("flatten"); return; }
+    if (flb_map_flatten_xyzi(map_, nullptr, 0, &n)) { report("flatten"); return; }
+    std::vector<float> o((size_t)std::max(n, 1) * 4);
+    if (flb_map_flatten_xyzi(map_, o.data(), n, &n)) { report("flatten"); return; }
     const size_t base = Storage.size();
     Storage.resize(base + n);
-    for (int i = 0; i < n; ++i) set(Storage[base + i], &o[3 * (size_t)i]);
+    for (int i = 0; i < n; ++i) set(Storage[base + i], &o[4 * (size_t)i]);
   }
   void acquire_removed_points(PointVector& removed_points) { (void)removed_points; }  // dead in the reference (laserMapping.cpp:1124-1130)
   BoxPointType tree_range() {
@@ -181,10 +182,13 @@ class KD_TREE {
     std::fprintf(stderr, "[fastlio_b200] %s\n", err_.c_str());
   }
   static const float* xyz(const PointVector& v) { return v.empty() ? nullptr : &v[0].x; }
-  static void set(PointType& p, const float* c) { std::memset(&p, 0, sizeof(PointType)); p.x = c[0]; p.y = c[1]; p.z = c[2]; }
+  // the map keeps x, y, z, intensity of every point (what FAST-LIO's map points carry: normals and curvature are zero,
+  // laserMapping.cpp:1101-1110); records handed back have those four fields set and the rest zeroed
+  static int off_intensity() { return (int)offsetof(PointType, intensity); }
+  static void set(PointType& p, const float* c) { std::memset(&p, 0, sizeof(PointType)); p.x = c[0]; p.y = c[1]; p.z = c[2]; p.intensity = c[3]; }
   static void fill(PointVector& out, const float* c, int n) {
     out.resize(n);
-    for (int i = 0; i < n; ++i) set(out[i], c + 3 * (size_t)i);
+    for (int i = 0; i < n; ++i) set(out[i], c + 4 * (size_t)i);
   }
 
   flb_map* map_ = nullptr;

@@ -124,6 +124,59 @@ void ikdref_delete_points(void* h, const float* xyz, int n) {
   static_cast<Tree*>(h)->Delete_Points(v);
 }
 
+// ---- the same with PointType::intensity (x, y, z, intensity records): the reference tree stores whole points
+static inline PointT mk4(const float* p) {
+  PointT q = mk(p);
+  q.intensity = p[3];
+  return q;
+}
+void ikdref_build_i(void* h, const float* xyzi, int n) {
+  PV v(n);
+  for (int i = 0; i < n; i++) v[i] = mk4(xyzi + 4 * i);
+  static_cast<Tree*>(h)->Build(v);
+}
+int ikdref_add_points_i(void* h, const float* xyzi, int n, int downsample_on) {
+  if (n <= 0) return 0;
+  PV v(n);
+  for (int i = 0; i < n; i++) v[i] = mk4(xyzi + 4 * i);
+  return static_cast<Tree*>(h)->Add_Points(v, downsample_on != 0);
+}
+int ikdref_flatten_i(void* h, float* out, int cap) {
+  Tree* t = static_cast<Tree*>(h);
+  PV st;
+  if (t->Root_Node == nullptr) return 0;
+  t->flatten(t->Root_Node, st, NOT_RECORD);
+  int n = (int)st.size();
+  if (out)
+    for (int i = 0; i < n && i < cap; i++) {
+      out[4 * i + 0] = st[i].x;
+      out[4 * i + 1] = st[i].y;
+      out[4 * i + 2] = st[i].z;
+      out[4 * i + 3] = st[i].intensity;
+    }
+  return n;
+}
+// k-NN returning the neighbours' intensities as well: out_xyzi[nq*k*4]
+void ikdref_nearest_i(void* h, const float* q, int nq, int k, float* out_xyzi, float* out_d2, int* out_cnt) {
+  Tree* t = static_cast<Tree*>(h);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < nq; i++) {
+    PV nn;
+    std::vector<float> d2;
+    t->Nearest_Search(mk(q + 3 * i), k, nn, d2);
+    int c = (int)nn.size();
+    out_cnt[i] = c;
+    for (int j = 0; j < k; j++) {
+      const size_t o = (size_t)i * k + j;
+      out_xyzi[4 * o] = j < c ? nn[j].x : NAN;
+      out_xyzi[4 * o + 1] = j < c ? nn[j].y : NAN;
+      out_xyzi[4 * o + 2] = j < c ? nn[j].z : NAN;
+      out_xyzi[4 * o + 3] = j < c ? nn[j].intensity : NAN;
+      out_d2[o] = j < c ? d2[j] : INFINITY;
+    }
+  }
+}
+
 int ikdref_size(void* h) { return static_cast<Tree*>(h)->size(); }
 int ikdref_validnum(void* h) { return static_cast<Tree*>(h)->validnum(); }
 

@@ -91,6 +91,12 @@ def ref():
         L.ikdref_has_root.restype = C.c_int
         L.ikdref_nearest_md.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_double, f32p, f32p, i32p]
         L.ikdref_delete_points.argtypes = [C.c_void_p, f32p, C.c_int]
+        L.ikdref_build_i.argtypes = [C.c_void_p, f32p, C.c_int]
+        L.ikdref_add_points_i.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int]
+        L.ikdref_add_points_i.restype = C.c_int
+        L.ikdref_flatten_i.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ikdref_flatten_i.restype = C.c_int
+        L.ikdref_nearest_i.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, f32p, f32p, i32p]
         _ref = L
     return _ref
 
@@ -212,6 +218,30 @@ class RefIkdTree(_MapBase):
     def Delete_Points(self, pts):
         pts = _xyz(pts)
         self._L.ikdref_delete_points(self.h, pts, len(pts))
+
+    # whole-PointType behaviour of the reference tree: x, y, z, intensity records in and out
+    def Build_xyzi(self, pts4):
+        a = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+        self._L.ikdref_build_i(self.h, a.reshape(-1), len(a))
+
+    def Add_Points_xyzi(self, pts4, downsample_on):
+        a = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+        return self._L.ikdref_add_points_i(self.h, a.reshape(-1), len(a), 1 if downsample_on else 0)
+
+    def flatten_xyzi(self):
+        n = self._L.ikdref_flatten_i(self.h, None, 0)
+        out = np.empty((max(n, 1), 4), np.float32)
+        n2 = self._L.ikdref_flatten_i(self.h, out.ctypes.data_as(C.c_void_p), n)
+        return out[:min(n, n2)].copy()
+
+    def Nearest_Search_xyzi(self, q, k=5):
+        q = _xyz(q)
+        n = len(q)
+        out = np.empty((n, k, 4), np.float32)
+        d2 = np.empty((n, k), np.float32)
+        cnt = np.empty(n, np.int32)
+        self._L.ikdref_nearest_i(self.h, q.reshape(-1), n, k, out.reshape(-1), d2.reshape(-1), cnt)
+        return out, d2, cnt
 
 
 class PortMap(_MapBase):

@@ -37,6 +37,7 @@ int main() {
   PointVector cloud;
   for (int i = 0; i < 60000; ++i) { PointType p{}; p.x = U(rng); p.y = U(rng); p.z = N(rng); cloud.push_back(p); }           // ground
   for (int i = 0; i < 30000; ++i) { PointType p{}; p.x = 6.f + N(rng); p.y = U(rng); p.z = 0.3f * (U(rng) + 10.f); cloud.push_back(p); }  // wall
+  for (size_t i = 0; i < cloud.size(); ++i) cloud[i].intensity = (float)(i % 251);   // whole records live in the map (ikd_Tree.h:64-86)
   ikdtree.set_capacity(1 << 20, 1 << 16);
   if (ikdtree.Root_Node != nullptr) return 2;
   ikdtree.set_downsample_param(0.2f);
@@ -50,6 +51,20 @@ int main() {
   float best = 1e30f;
   for (auto& p : cloud) { float d = (p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y) + (p.z - q.z) * (p.z - q.z); if (d < best) best = d; }
   if (best != d2[0]) return 5;
+  // the neighbours come back with their intensity (Nearest_Points are whole PointType records, ikd_Tree.cpp:391-395)
+  for (auto& nb : near) {
+    bool ok = false;
+    for (auto& p : cloud) if (p.x == nb.x && p.y == nb.y && p.z == nb.z) { ok = p.intensity == nb.intensity; break; }
+    if (!ok) return 40;
+  }
+  {
+    PointVector all;
+    ikdtree.flatten(ikdtree.Root_Node, all, NOT_RECORD);
+    double si = 0, so = 0;
+    for (auto& p : cloud) si += p.intensity;
+    for (auto& p : all) so += p.intensity;
+    if (all.size() != cloud.size() || si != so) return 41;
+  }
   PointVector add = cloud; add.resize(2000);
   for (auto& p : add) p.z += 0.05f;
   ikdtree.Add_Points(add, true);

@@ -56,9 +56,13 @@ def test_capacity_exhaustion_fails_loudly(scene):
     with pytest.raises(capi.FlbError, match="block pool exhausted|error flags"):
         t.Build(scene["map"])
     t.close()
+    # a NaN / unrepresentable point is skipped with a warning, it does not poison the map (the reference keeps running too):
+    # the call succeeds, the good points are in, and later calls keep working
     t = capi.KDTree(voxel_size=0.2, max_points=1 << 20, max_blocks=1 << 17)
-    with pytest.raises(capi.FlbError, match="range|error flags"):
-        t.Build(np.array([[0, 0, 0], [np.nan, 0, 0]], np.float32))
+    t.Build(np.array([[0, 0, 0], [np.nan, 0, 0], [1e12, 0, 0], [1, 1, 1]], np.float32))
+    assert t.validnum() == 2
+    assert t.Add_Points(np.array([[2, 2, 2], [np.inf, 0, 0]], np.float32), True) == 1
+    assert t.validnum() == 3 and len(t.flatten()) == 3
     t.close()
     # scan larger than the session capacity
     t = capi.KDTree(voxel_size=0.2, max_points=1 << 18, max_blocks=1 << 14)
@@ -223,3 +227,62 @@ def test_map_destroyed_before_session_is_safe(scene):
     s, P, st = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
     assert st["passes"] == 4
     ses.close()
+
+
+def _rows4(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def test_intensity_travels_with_map_points(scene, oracle):
+    """The reference tree stores whole PointType records (ikd_Tree.h:64-86): intensity comes back from flatten (featsFromMap,
+    laserMapping.cpp:2361-2367) and Nearest_Search.  Same operations on the reference ikd-Tree compiled unmodified:
+    verbatim Build (multi-point voxels), downsampled Add_Points (voxel winners keep THEIR intensity), verbatim Add_Points, a box
+    delete (overflow nodes move into head slots), then a scan inserted through map_incremental."""
+    if not oracle.have_ref():
+        pytest.skip("reference ikd-Tree not built")
+    rng = np.random.default_rng(11)
+    mp = scene["map"]
+    m4 = np.column_stack([mp, rng.uniform(0, 255, len(mp)).astype(np.float32)]).astype(np.float32)
+    t = capi.KDTree(voxel_size=scene["ds"], max_points=1 << 21, max_blocks=1 << 18)
+    ref = oracle.RefIkdTree(ds=scene["ds"])
+    half = len(m4) // 2
+    t.Build_xyzi(m4[:half])
+    ref.Build_xyzi(m4[:half])
+    assert np.array_equal(_rows4(t.flatten_xyzi()), _rows4(ref.flatten_xyzi()))
+    t.Add_Points_xyzi(m4[half:], True)
+    ref.Add_Points_xyzi(m4[half:], True)
+    extra = (m4[:3000] + np.array([0.01, 0.0, 0.0, 1.0], np.float32)).astype(np.float32)
+    t.Add_Points_xyzi(extra, False)
+    ref.Add_Points_xyzi(extra, False)
+    assert np.array_equal(_rows4(t.flatten_xyzi()), _rows4(ref.flatten_xyzi()))
+    box = np.array([[-8, -8, -3, 8, 8, 1]], np.float32)
+    assert t.Delete_Point_Boxes(box) == ref.Delete_Point_Boxes(box)
+    fg, fr = _rows4(t.flatten_xyzi()), _rows4(ref.flatten_xyzi())
+    assert np.array_equal(fg, fr) and len(fg) == t.validnum()
+    # neighbours carry their intensity (compared where the 5 distances are distinct: ties may be ordered differently)
+    q = (mp[::97] + rng.normal(0, 0.05, (len(mp[::97]), 3))).astype(np.float32)
+    og, dg, cg = t.Nearest_Search_xyzi(q, 5)
+    orf, dr, cr = ref.Nearest_Search_xyzi(q, 5)
+    assert np.array_equal(cg, cr) and np.array_equal(dg, dr)
+    distinct = (np.diff(dg, axis=1) > 0).all(axis=1)
+    assert distinct.sum() > 100 and np.array_equal(og[distinct], orf[distinct])
+    # a scan with intensities through the update + map_incremental: the inserted world points keep the scan's intensity
+    body = scene["body"]
+    b4 = np.column_stack([body, np.arange(len(body), dtype=np.float32) % 199]).astype(np.float32)
+    ses = capi.Session(t, max_scan_points=len(body), max_iterations=3)
+    ses.scan_upload_xyzi(b4)
+    s, P, st = ses.update_iterated_dyn_share_modified(scene["prior"], scene["P"])
+    before = {tuple(r) for r in t.flatten_xyzi().tolist()}
+    a, b = ses.map_incremental(s)
+    after = t.flatten_xyzi()
+    new = np.array([r for r in after.tolist() if tuple(r) not in before], np.float32)
+    assert a + b > 0 and len(new) > 0
+    world = synth.body_to_world_np(s, body)
+    lut = {tuple(w): i for w, i in zip(world.tolist(), b4[:, 3].tolist())}
+    hit = [lut.get(tuple(r[:3])) for r in new.tolist()]
+    known = [(h, r[3]) for h, r in zip(hit, new.tolist()) if h is not None]
+    assert len(known) > 0.9 * len(new) and all(h == v for h, v in known)
+    ses.close()
+    t.close()
+    ref.close()

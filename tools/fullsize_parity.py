@@ -65,6 +65,11 @@ def main():
     P0 = work["P"]
     for k in range(args.frames):
         body = work["scans"][k]
+        # the same scan through the HOST-driven engine first (update only: the map is not touched), as a third opinion
+        ses.scan_upload(body)
+        ses.set_update_engine(False)
+        s_h, P_h, st_h = ses.update_iterated_dyn_share_modified(work["priors"][k], P0)
+        ses.set_update_engine(True)
         s_g, P_g, r = ses.scan_step(fov_g, body, work["priors"][k], P0, True)
         nb = ses.neighbors()
         boxes = fov_c.step(pos_lid_c)
@@ -83,7 +88,11 @@ def main():
         rec = {"k": k, "dpos": float(np.abs(s_g[:3] - s_c[:3]).max()), "dpos_l2": float(np.linalg.norm(s_g[:3] - s_c[:3])),
                "dq": float(np.abs(s_g[3:7] - s_c[3:7]).max()), "dstate": float(np.abs(s_g - s_c).max()),
                "dP": float(np.abs(P_g - P_c).max()),
+               "dpos_host_engine_vs_cpu": float(np.abs(s_h[:3] - s_c[:3]).max()),
+               "dpos_host_engine_vs_device_engine": float(np.abs(s_h[:3] - s_g[:3]).max()),
+               "host_engine": {k2: st_h[k2] for k2 in ("passes", "search_passes", "effct_feat_num", "converged_count")},
                "gpu": {"passes": r.update.passes, "searches": r.update.search_passes, "M": r.update.effct_feat_num,
+                       "t": r.update.converged_count,
                        "add": r.n_to_add, "no_ds": r.n_no_downsample, "valid": r.map_valid, "deleted": r.n_deleted},
                "cpu": {"stats": [int(x) for x in st], "add": na, "no_ds": nn, "valid": ref.validnum()},
                "nbr_rows_diff": nbr_diff, "world_rows_diff": world_diff, "sel_diff": sel_diff, "cnt_diff": cnt_diff,
@@ -99,7 +108,8 @@ def main():
             rec["map_only_gpu_pts"] = [list(map(float, p)) for p in og[:10].tolist()]
             rec["map_only_ref_pts"] = [list(map(float, p)) for p in oc[:10].tolist()]
         out["frames"].append(rec)
-        bench.log(json.dumps({a: rec[a] for a in ("k", "dpos", "dq", "nbr_rows_diff", "world_rows_diff", "sel_diff")}),
+        bench.log(json.dumps({a: rec[a] for a in ("k", "dpos", "dq", "dpos_host_engine_vs_cpu", "dpos_host_engine_vs_device_engine", "nbr_rows_diff", "sel_diff")}),
+                  rec["gpu"]["t"], rec["host_engine"]["converged_count"], rec["cpu"]["stats"][3],
                   rec.get("map_only_gpu"), rec.get("map_only_ref"), rec["gpu"]["valid"], rec["cpu"]["valid"])
     out["max_dpos"] = max(f["dpos"] for f in out["frames"])
     out["max_dq"] = max(f["dq"] for f in out["frames"])

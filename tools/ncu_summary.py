@@ -53,5 +53,42 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst):
+    """dram bytes (read + write) of ONE 5-NN search pass = the first captured k_knn_stencil + the k_knn that follows it;
+    stamped with the md5 of csrc/knn_kernels.cuh so that bench.py drops the number once the kernels change."""
+    import hashlib
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(raw.splitlines()))
+    hdr, units = r[0], r[1]
+    ik, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+
+    def tobytes(v, u):
+        v = float(v.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    rows = r[2:]
+    best = None
+    for i, row in enumerate(rows):   # the heaviest stencil launch = a search pass; add the exact kernel right after it
+        if "k_knn_stencil" in row[ik]:
+            t = float(row[it].replace(",", ""))
+            if best is None or t > best[0]:
+                best = (t, i)
+    if best is None:
+        raise SystemExit("no k_knn_stencil launch in " + src)
+    i = best[1]
+    tot = tobytes(rows[i][ir], units[ir]) + tobytes(rows[i][iw], units[iw])
+    names = [rows[i][ik]]
+    if i + 1 < len(rows) and "k_knn<" in rows[i + 1][ik]:
+        tot += tobytes(rows[i + 1][ir], units[ir]) + tobytes(rows[i + 1][iw], units[iw])
+        names.append(rows[i + 1][ik])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md5 = hashlib.md5(open(os.path.join(root, "better_fastlio2_b200", "csrc", "knn_kernels.cuh"), "rb").read()).hexdigest()
+    json.dump({"dram_bytes_per_launch": tot, "kernels": names, "source": os.path.basename(src), "knn_kernels_md5": md5,
+               "what": "dram__bytes_read.sum + dram__bytes_write.sum of one 5-NN search pass (k_knn_stencil + k_knn), ncu --set full, cold cache"},
+              open(dst, "w"), indent=1)
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
