@@ -552,7 +552,7 @@ def run_b200(args):
             "device_bytes": int(stats.get("device_bytes", 0)),
             "e2e": {"value": aggregate_scans_per_s(world_size, K, e2e_ms), "unit": "scans/s",
                     "h2d_bytes_per_step": int(16 * n_mean), "d2h_bytes_per_step": int(passes / K * 93 * 8 + 2 * 128 + 8)},
-            "roofline": {"bound": "hbm", "kernel": "k_knn_stencil<5> + k_knn<5,32> (one 5-NN search pass)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_knn_stencil<5> + k_knn<5> (one 5-NN search pass)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": knn_traffic(),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                          "alg_bytes_per_launch": ALG_BYTES_PER_QUERY_SEARCH * (npts_prof / PROF), "avg_launch_ms": knn_ms,

@@ -131,13 +131,15 @@ def run_cfg3(args):
     # and their poses (x, y, z, roll, pitch, yaw of the posterior)
     kf_clouds, kf_poses = [], []
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    step_ms, recon_ms, recon_pts, errs, launches = 0.0, [], [], [], 0
+    step_ms, recon_ms, recon_pts, errs, launches, step_lat = 0.0, [], [], [], 0, []
     seg_start = 0
     ev[0].record(stream)
     for k in range(NS):
         st, P = priors[k].copy(), work["P"].copy()
         ses.scan_set_device(dev[k].data_ptr(), len(scans[k]))
+        t_s = time.perf_counter()
         r = ses.scan_step_ptr(fov, None, 0, 0, st, P)
+        step_lat.append(time.perf_counter() - t_s)
         launches += r.kernel_launches
         errs.append(float(np.linalg.norm(st[:3] - truths[k][:3])))
         R = synth.quat_to_mat(st[3:7])
@@ -159,9 +161,23 @@ def run_cfg3(args):
     ev[1].record(stream)
     torch.cuda.synchronize()
     step_ms += ev[0].elapsed_time(ev[1])
+    # where the time goes: per-kernel-class CUDA events over 5 further steps (direct-launch path, frames re-used)
+    tree.profile_enable(True)
+    for k in range(NS - 5, NS):
+        st, P = priors[k].copy(), work["P"].copy()
+        ses.scan_set_device(dev[k].data_ptr(), len(scans[k]))
+        ses.scan_step_ptr(fov, None, 0, 0, st, P)
+    prof = tree.profile_read(reset=True)
+    tree.profile_enable(False)
+    out["kernel_ms_per_step"] = {k: prof[k]["ms"] / 5 for k in capi.K_CLASSES}
+    out["knn_phase_fraction"] = [x / max(sum(prof["knn_phase"]), 1) for x in prof["knn_phase"]]
     stats = tree.stats()
     out.update({"value": NS / (step_ms * 1e-3), "ms_per_step": step_ms / NS, "steps": NS, "gpu_launches": launches,
                 "scan_points_mean": float(np.mean([len(s) for s in scans])),
+                "step_ms": {"p50": float(np.percentile(step_lat, 50) * 1e3), "p90": float(np.percentile(step_lat, 90) * 1e3),
+                            "max": float(np.max(step_lat) * 1e3), "after_reconstruct": [float(step_lat[i] * 1e3) for i in (KD_STEP, KD_STEP + 1, KD_STEP + 2) if i < NS],
+                            "what": "host clock around each step call (device-resident scan); the steps right after a recontructIKdTree run "
+                                    "against the 10 m sub-map: most of the 100 m scan then has no map behind it"},
                 "reconstruct": {"every": KD_STEP, "ms": recon_ms, "submap_points": recon_pts,
                                 "what": "recontructIKdTree data path: key-frame clouds (host, 48-B PointType) -> transform -> VoxelGrid(0.2) -> "
                                         "reconstruct, wall clock incl. the upload"},

@@ -6,6 +6,7 @@
 #include "knn_kernels.cuh"
 #include "meas_kernels.cuh"
 #include "esikf_device.cuh"
+#include "knn_tile.cuh"
 #include "esikf_host.hpp"
 
 #include <cub/device/device_scan.cuh>
@@ -120,6 +121,9 @@ struct flb_map {
   int* worklist = nullptr;       // unresolved-query list of the stencil k-NN kernel
   int work_cap = 0;
   bool scratch_clean = false;    // the downsample scratch hash was already cleared off the critical path (scan graph)
+  unsigned char* kf_raw = nullptr;   // flb_map_reconstruct_keyframes scratch (grow-only)
+  float4 *kf_in = nullptr, *kf_out = nullptr;
+  size_t kf_raw_cap = 0, kf_pts_cap = 0;
   int gen = 0;                   // bumped whenever a buffer or parameter baked into a captured scan graph changes (scratch hash,
                                  // work list, voxel size): sessions re-capture their graphs on a mismatch
   bool warned_range = false;
@@ -221,7 +225,8 @@ extern "C" int flb_map_create(const flb_map_config* cfg, flb_map** out) {
   d.ds = cfg->voxel_size;
   d.block_cap = m->cfg.max_blocks;
   d.ovf_cap = std::max(1024, m->cfg.max_points / 2);
-  m->hash_cap = next_pow2((uint64_t)d.block_cap * 2);
+  // load factor <= 1/4 at full capacity (typically 5-10 % in use): a probe rarely continues past its home slot
+  m->hash_cap = next_pow2((uint64_t)d.block_cap * 4);
   m->chash_cap = next_pow2(std::max<uint64_t>(1024, (uint64_t)d.block_cap / 8));
   d.hash_mask = m->hash_cap - 1;
   d.chash_mask = m->chash_cap - 1;
@@ -266,7 +271,7 @@ static void map_release(flb_map* m) {
   if (m->stream) Q(cudaStreamSynchronize(m->stream));
   MapDev& d = m->d;
   void* ptrs[] = {d.clist, d.hent, d.bslot, d.slots, d.sint, d.oint, d.ovf, d.bkey, d.brel, d.free_blk, d.free_ovf, d.ckeys, d.cbits, d.counters,
-                  m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist};
+                  m->d_misc, m->stage, m->raw, m->skeys, m->sbest, m->dparams, m->outbuf, m->d_phase, m->worklist, m->kf_raw, m->kf_in, m->kf_out};
   for (void* p : ptrs) if (p) Q(cudaFree(p));
   if (m->h_counters) Q(cudaFreeHost(m->h_counters));
   for (auto& r : m->prof_pool) { Q(cudaEventDestroy(r.a)); Q(cudaEventDestroy(r.b)); }
@@ -725,6 +730,63 @@ extern "C" int flb_map_profile_read(flb_map* m, flb_profile* out, int reset) {
   for (int i = 0; i < 4; ++i) out->knn_phase[i] = ph[i];
   out->knn_chain_nodes = ph[4]; out->knn_chain_max = ph[5]; out->knn_head_candidates = ph[6];
   if (reset) { m->prof_used = 0; CU(cudaMemset(m->d_phase, 0, sizeof(int) * 8)); }
+  return 0;
+}
+
+// A/B harness of the stencil 5-NN kernel variants (tools/knn_tile_ab.py; not on the product path): nq queries, `iters`
+// timed launches (CUDA events on the map's stream) of variant 0 = k_knn_stencil<5>, 1 = k_knn_tile<5> (bulk-copy staged
+// buckets).  out_d2[nq*5] / out_cnt[nq] (optional) return the variant's raw result (before the exact completion kernel).
+extern "C" int flb_debug_knn_bench(flb_map* m, const float* q_xyz, int nq, int stride, int variant, int iters, float* ms_per_launch,
+                                   int* unresolved, float* out_d2, int* out_cnt) {
+  if (!m || !q_xyz || nq <= 0 || iters <= 0) return set_err("flb_debug_knn_bench: bad argument");
+  CU(cudaSetDevice(m->cfg.device));
+  if (upload_points(m, q_xyz, nq, stride)) return 1;
+  if (ensure_outbuf(m, nq * 5)) return 1;
+  if (nq > m->work_cap) {
+    if (m->worklist) cudaFree(m->worklist);
+    m->worklist = nullptr; m->work_cap = 0;
+    CU(cudaMalloc((void**)&m->worklist, sizeof(int) * (size_t)std::max(nq, 1 << 17)));
+    m->work_cap = std::max(nq, 1 << 17);
+    m->gen++;
+  }
+  unsigned char* dcnt = nullptr;
+  CU(cudaMalloc((void**)&dcnt, nq));
+  KnnArgs a;
+  a.m = m->d; a.q = m->stage; a.n = nq; a.nbr = m->outbuf; a.cnt = dcnt; a.max_d2 = INFINITY; a.phase_stats = nullptr;
+  a.worklist = m->worklist; a.work_count = m->d_misc + 12; a.work_ticket = m->d_misc + 13; a.ctl = nullptr; a.body = nullptr; a.stride = nq;
+  cudaError_t e = cudaFuncSetAttribute(k_knn_tile<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  const int grid = (nq + 127) / 128;
+  for (int it = -2; it < iters && e == cudaSuccess; ++it) {
+    if (it == 0) e = cudaEventRecord(e0, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.work_count, 0, 2 * sizeof(int), m->stream);
+    if (variant == 0) k_knn_stencil<5><<<grid, 128, 0, m->stream>>>(a);
+    else k_knn_tile<5><<<grid, TILE_THREADS, sizeof(TileSmem), m->stream>>>(a);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(e1, m->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_per_launch) *ms_per_launch = ms / (float)iters;
+  if (e == cudaSuccess && unresolved) e = cudaMemcpy(unresolved, a.work_count, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && out_d2) {
+    std::vector<float4> h((size_t)nq * 5);
+    e = cudaMemcpy(h.data(), m->outbuf, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < nq && e == cudaSuccess; ++i)
+      for (int j = 0; j < 5; ++j) out_d2[(size_t)i * 5 + j] = h[(size_t)j * nq + i].w;
+  }
+  if (e == cudaSuccess && out_cnt) {
+    std::vector<unsigned char> hc(nq);
+    e = cudaMemcpy(hc.data(), dcnt, nq, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < nq; ++i) out_cnt[i] = hc[i];
+  }
+  cudaFree(dcnt);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e != cudaSuccess) return set_err("flb_debug_knn_bench: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -362,9 +362,24 @@ extern "C" int flb_map_reconstruct_keyframes(flb_map* m, const void* const* clou
   float4 *in = nullptr, *out = nullptr;
   auto body = [&]() -> int {
     if (n == 0) return map_reset_storage(m);   // reconstruct with an empty cloud: everything deleted
-    CU(cudaMalloc((void**)&raw, (size_t)n * stride));
-    CU(cudaMalloc((void**)&in, sizeof(float4) * (size_t)n));
-    CU(cudaMalloc((void**)&out, sizeof(float4) * (size_t)n));
+    // scratch of the sub-map assembly: kept with the map and only ever grown (recontructIKdTree runs every kd_step key frames
+    // with clouds of similar size; cudaMalloc / cudaFree of ~200 MB per call cost more than the kernels)
+    const size_t need_raw = (size_t)n * stride, need_pts = sizeof(float4) * (size_t)n;
+    if (need_raw > m->kf_raw_cap) {
+      if (m->kf_raw) Q(cudaFree(m->kf_raw));
+      m->kf_raw = nullptr; m->kf_raw_cap = 0;
+      CU(cudaMalloc((void**)&m->kf_raw, need_raw + need_raw / 4));
+      m->kf_raw_cap = need_raw + need_raw / 4;
+    }
+    if (need_pts > m->kf_pts_cap) {
+      if (m->kf_in) Q(cudaFree(m->kf_in));
+      if (m->kf_out) Q(cudaFree(m->kf_out));
+      m->kf_in = m->kf_out = nullptr; m->kf_pts_cap = 0;
+      CU(cudaMalloc((void**)&m->kf_in, need_pts + need_pts / 4));
+      CU(cudaMalloc((void**)&m->kf_out, need_pts + need_pts / 4));
+      m->kf_pts_cap = need_pts + need_pts / 4;
+    }
+    raw = m->kf_raw; in = m->kf_in; out = m->kf_out;
     // *subMapKeyFrames += *transformPointCloud(surfCloudKeyFrames[k], &cloudKeyPoses6D->points[k])  (laserMapping.cpp:636)
     size_t off = 0;
     for (int k = 0; k < n_kf; ++k) {
@@ -396,9 +411,6 @@ extern "C" int flb_map_reconstruct_keyframes(flb_map* m, const void* const* clou
     return 0;
   };
   const int rc = body();
-  if (raw) Q(cudaFree(raw));
-  if (in) Q(cudaFree(in));
-  if (out) Q(cudaFree(out));
   vg_release(w);
   return rc;
 }

@@ -473,6 +473,13 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
     FLB_DBG_CLOCK(e0);
     int dbg_rings = 0;
     (void)dbg_rings;
+#ifdef FLB_TRACE
+    long long ph_probe = 0, ph_push = 0, ph_load = 0, ph_merge = 0, ph_mark = clock64();
+    const long long ph_seed = ph_mark - e0;
+#define KPH(acc) { const long long now_ = clock64(); acc += now_ - ph_mark; ph_mark = now_; }
+#else
+#define KPH(acc)
+#endif
 #pragma unroll 1
     for (int r = 1; r <= EXACT_RINGS && !done; ++r) {
       if (r == 3) {
@@ -515,9 +522,11 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
               go = (cb[cell * 8 + (bit >> 6)] >> (bit & 63)) & 1ull;
             }
             if (go) {
-              const HEntry* he = &m.hent[hash_key(pack_key(bx, by, bz)) & m.hash_mask];
+              const uint32_t hs = hash_key(pack_key(bx, by, bz)) & m.hash_mask;
+              const HEntry* he = &m.hent[hs];
               ent[u] = __ldg(reinterpret_cast<const uint4*>(he));
               mask[u] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));   // same 32-B sector
+              prefetch_next_entry(m, hs);
               blk[u] = -1;
             }
           }
@@ -540,6 +549,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
           } else mask[u] = 0ull;
           c += __popcll(mask[u]);
         }
+        KPH(ph_probe);
         // ---- compaction: exclusive prefix of the per-lane candidate counts
         int incl = c;
 #pragma unroll
@@ -565,6 +575,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
             }
           }
           __syncwarp();
+          KPH(ph_push);
           const int n = min(T - chunk, CAND_CAP);
 #pragma unroll 1
           for (int j0 = 0; j0 < n; j0 += 128) {
@@ -590,10 +601,13 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
             }
           }
           __syncwarp();
+          KPH(ph_load);
         }
       }
+      KPH(ph_probe);
       // ---- merge the lane-local lists: new k-th distance, completeness of the searched cube
       gcount = warp_merge<K>(t, FULL, lane, lane, rd, rx, ry, rz, thr);
+      KPH(ph_merge);
       dbg_rings = r;
       const float cov = cover2(qx, qy, qz, (float)(qbx - r) * bs4, (float)(qby - r) * bs4, (float)(qbz - r) * bs4,
                                (float)(qbx + r + 1) * bs4, (float)(qby + r + 1) * bs4, (float)(qbz + r + 1) * bs4, mg);
@@ -611,6 +625,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       const long long e1 = clock64();
       FLB_DBG_ADD(16, 1); FLB_DBG_ADD(17, e1 - e0); FLB_DBG_MAX(18, e1 - e0); FLB_DBG_ADD(18 + min(dbg_rings, 6), 1);
       FLB_DBG_ADD(25, done ? 0 : 1);
+      FLB_DBG_ADD(32, ph_seed); FLB_DBG_ADD(33, ph_probe); FLB_DBG_ADD(34, ph_push); FLB_DBG_ADD(35, ph_load); FLB_DBG_ADD(36, ph_merge);
     }
 #endif
     // ---------------- still unresolved after the block rings: finish over the coarse levels (the blocks of the rings
@@ -848,9 +863,11 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     unsigned long long occ[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const HEntry* he = &m.hent[hash_key(pack_key(bbx + (b & 1), bby + ((b >> 1) & 1), bbz + (b >> 2))) & m.hash_mask];
+      const uint32_t hs = hash_key(pack_key(bbx + (b & 1), bby + ((b >> 1) & 1), bbz + (b >> 2))) & m.hash_mask;
+      const HEntry* he = &m.hent[hs];
       ent[b] = __ldg(reinterpret_cast<const uint4*>(he));
       occ[b] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));
+      prefetch_next_entry(m, hs);
     }
     int blk8[8];
 #pragma unroll

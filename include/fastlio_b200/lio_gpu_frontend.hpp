@@ -45,10 +45,12 @@ class LioGpu {
   }
   void set_row_mode(RowMode m) { mode_ = m; }
 
-  // feats_down_body (laserMapping.cpp:2322-2325)
-  bool begin_scan(const float* first_xyz, int n, int stride_bytes) {
+  // feats_down_body (laserMapping.cpp:2322-2325).  off_intensity: byte offset of PointType::intensity inside a record
+  // (offsetof(PointType, intensity)); the intensity then travels with the point into the map, as pointBodyToWorld copies it
+  // (laserMapping.cpp:1101-1110).  < 0: xyz only.
+  bool begin_scan(const float* first_xyz, int n, int stride_bytes, int off_intensity = -1) {
     n_ = n;
-    if (flb_scan_upload(ses_, first_xyz, n, stride_bytes)) { std::fprintf(stderr, "[fastlio_b200] %s\n", flb_last_error()); return false; }
+    if (flb_scan_upload_pt(ses_, first_xyz, n, stride_bytes, off_intensity)) { std::fprintf(stderr, "[fastlio_b200] %s\n", flb_last_error()); return false; }
     return true;
   }
 

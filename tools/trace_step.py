@@ -114,6 +114,10 @@ def main():
               f"queries/step={nq / S:.0f} cycles/query={dbg_sum[17] / nq:.0f} max={dbg_max[18]:.0f} "
               f"done after ring1/2/3={dbg_sum[19] / nq:.3f}/{dbg_sum[20] / nq:.3f}/{dbg_sum[21] / nq:.3f} coarse={dbg_sum[25] / nq:.4f} "
               "")
+        if dbg_sum[32] > 0:
+            print("# exact kernel, cycles/query by phase: " + ", ".join(
+                f"{nm}={dbg_sum[i] / nq:.0f}" for nm, i in (("ticket+seed loads", 32), ("enumerate+probe", 33), ("compaction push", 34),
+                                                            ("point loads+insert", 35), ("merge", 36))))
     out["dbg_sum"] = dbg_sum.tolist()
     out["dbg_max"] = dbg_max.tolist()
     if args.out:
