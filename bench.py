@@ -469,12 +469,15 @@ def run_b200(args):
 
     row_lo = clocks.mark()
     blocks = [timed_block(idx) for idx in cycle_blocks(w0)]            # cycle 0: the blocks after the parity frames
+    blocks_per_cycle = [len(blocks)]
     first_ms = dist_max([float(np.median([b[0] for b in blocks]))], device=devname)[0]
     nblocks = block_plan(first_ms) if not (TINY or NCU_SHORT) else (2 if TINY else 1)
     while len(blocks) < nblocks:
         w, _ = begin_cycle(False)
+        n0 = len(blocks)
         for idx in cycle_blocks(w):
             blocks.append(timed_block(idx))
+        blocks_per_cycle.append(len(blocks) - n0)
     row_hi = clocks.mark()
     ms_blocks = np.array(dist_max([b[0] for b in blocks], device=devname))   # per block: max over ranks
     order = np.argsort(ms_blocks)
@@ -538,6 +541,7 @@ def run_b200(args):
                                "library stream, max over ranks per block; value = median block",
                        "blocks": len(blocks), "block_ms_median": ms, "block_ms_min": float(ms_blocks.min()),
                        "block_ms_max": float(ms_blocks.max()), "device_ms_total": float(ms_blocks.sum()),
+                       "block_ms": [round(float(x), 4) for x in ms_blocks], "blocks_per_cycle": blocks_per_cycle,
                        "value_min": aggregate_scans_per_s(world_size, K, float(ms_blocks.max())),
                        "value_max": aggregate_scans_per_s(world_size, K, float(ms_blocks.min())),
                        "e2e_blocks": len(eblocks), "e2e_block_ms_min": float(e2e_ms_blocks.min()),
@@ -545,6 +549,7 @@ def run_b200(args):
             "per_rank": [{"rank": i, "block_ms_median": r[0], "block_ms_min": r[1], "block_ms_max": r[2], "e2e_block_ms_median": r[3],
                           "sm_mhz": r[4], "sm_max_mhz": r[5], "throttle_reasons": int(r[6])} for i, r in enumerate(per_rank)],
             "slowest_rank": int(np.argmax([r[0] for r in per_rank])),
+            "sum_of_rank_rates": float(sum(K / (r[0] * 1e-3) for r in per_rank)),   # (each rank's own median block; NOT the headline)
             "gpu_launches": launches,
             "latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3),
                            "max": float(lat.max() * 1e3), "samples": int(len(lat)),

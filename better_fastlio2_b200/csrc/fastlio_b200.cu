@@ -376,8 +376,15 @@ static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls
   }
   if (mode == 0 || mode == 2) {
     launch_k(k_append_points, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev);
-    launch_k(k_relocate_chains, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev);
-    m->launches += 2;
+    m->launches++;
+    // Chain relocation is a pure layout optimisation (contiguous overflow chains for the k-NN readers).  It pays after a bulk
+    // verbatim insert (Build, Add_Points(false): many multi-point voxels); map_incremental's verbatim class is a few hundred
+    // points per scan that land in (almost always) EMPTY voxels — nothing to re-lay — so the scan path leaves it out
+    // (6.4 us + a launch gap per scan on cfg2); chains stay valid linked lists either way.
+    if (!prefused) {
+      launch_k(k_relocate_chains, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev);
+      m->launches++;
+    }
   }
   CU(cudaGetLastError());
   if (!n_dev) m->has_root = true;

@@ -163,7 +163,13 @@ __device__ __forceinline__ bool esti_plane_dev(const float (&P)[5][3], float thr
 }
 
 // ---------------------------------------------------------------------------------------------- K1': residual + H^T H
-constexpr int MEAS_THREADS = 512;   // one CTA per SM: half as many per-block partials for the update kernel to reduce
+// One CTA per SM (148 block partials for the update kernel to reduce).  896 threads = 132 608 over the grid: a 120k-point scan
+// is ONE round of the point loop (512 threads needed two, the second 57 % full); the price is a 72-register cap (a few spilled
+// values in the QR).  Measured on cfg2 (profiles/r2j_*): 512 -> 3280, 768 -> 3161, 896 -> 3352 scans/s.
+#ifndef FLB_MEAS_THREADS
+#define FLB_MEAS_THREADS 896
+#endif
+constexpr int MEAS_THREADS = FLB_MEAS_THREADS;
 constexpr int NACC = 93;  // 91 upper-triangular entries of [h_x | h]^T [h_x | h] (13x13) + total_residual + M
 
 struct MeasArgs {
