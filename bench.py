@@ -119,6 +119,7 @@ def workload_config():
             "seed": SEED, "n_scans": n_scans_default(), "parity_frames": parity_frames_default(),
             "frame_schedule": "cycle 0: frames 0..parity_frames-1 from the fresh map (untimed, checked against the CPU replay), "
                               "then blocks of K consecutive frames; later cycles: map rebuilt (untimed), W warm-up frames, blocks of K",
+            "pipeline": "replay: two steps in flight",
             "l2_policy": "inputs larger than L2: ~480 MB of map block storage + a new 1.9 MB scan every step",
             "reference_arm": f"same workload and frame schedule; steps capped at {REF_STEPS_CAP} (bounded CPU sample)"}
 
@@ -421,19 +422,31 @@ def run_b200(args):
     # ---------------- timed region 1: inputs resident in HBM (value).  One block = EXACTLY K steps between a barrier +
     # synchronize on both sides, timed with CUDA events on the library stream; blocks are repeated (over as many cycles as
     # needed) until >= 0.5 s of device time has been measured and the MEDIAN block (of the max over ranks) is reported.
-    def timed_block(idx):
+    def timed_block(idx, pipelined=True):
         # the harness keeps its own work out of the timed loop (a C++ caller has none): states/covariances are staged
         # beforehand, results are inspected afterwards
         sts = [work["priors"][k].copy() for k in idx]
         Ps = [P0.copy() for _ in idx]
         res = [None] * K
         f = fov_box[0]
+        begin, finish = ses.scan_step_begin, ses.scan_step_finish
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
-        for j in range(K):
-            set_dev(dptr_all[idx[j]], nk_all[idx[j]])
-            res[j] = step_ptr(f, None, 0, 0, sts[j], Ps[j])
+        if pipelined:
+            # two steps in flight: scan j+1 is enqueued (its prior is known: replay) before scan j's posterior is collected,
+            # so the GPU never waits for the host between scans
+            set_dev(dptr_all[idx[0]], nk_all[idx[0]])
+            begin(f, sts[0], Ps[0], True)
+            for j in range(K):
+                if j + 1 < K:
+                    set_dev(dptr_all[idx[j + 1]], nk_all[idx[j + 1]])
+                    begin(f, sts[j + 1], Ps[j + 1], True)
+                res[j] = finish(f, sts[j], Ps[j])
+        else:
+            for j in range(K):
+                set_dev(dptr_all[idx[j]], nk_all[idx[j]])
+                res[j] = step_ptr(f, None, 0, 0, sts[j], Ps[j])
         e1.record(stream)
         barrier()
         perr = max(float(np.linalg.norm(sts[j][:3] - work["truths"][idx[j]][:3])) for j in range(K))
@@ -442,11 +455,11 @@ def run_b200(args):
     # ---------------- timed region 2: host buffers through the C ABI (e2e).  Streaming use of the public API: every
     # step's scan is copied from pinned host memory inside the region (flb_scan_prefetch, overlapping the previous
     # step's kernels) and every step's posterior state / covariance / counters are read back to the host.
-    def e2e_block(idx):
+    def e2e_block(idx, pipelined=True):
         sts2 = [work["priors"][k].copy() for k in idx]
         Ps2 = [P0.copy() for _ in idx]
-        pptr = [pptr_all[k] for k in idx] + [0]
-        pn = [nk_all[k] for k in idx] + [0]
+        pptr = [pptr_all[k] for k in idx] + [0, 0]
+        pn = [nk_all[k] for k in idx] + [0, 0]
         res2 = [None] * K
         lat = np.empty(K)
         f = fov_box[0]
@@ -454,14 +467,28 @@ def run_b200(args):
         t0 = time.perf_counter()
         ses.scan_prefetch_ptr(pptr[0], pn[0], 16)
         tp = t0
-        for j in range(K):
-            ses.scan_step_begin(f, sts2[j], Ps2[j], True)
-            if j + 1 < K:
-                ses.scan_prefetch_ptr(pptr[j + 1], pn[j + 1], 16)
-            res2[j] = ses.scan_step_finish(f, sts2[j], Ps2[j])
-            tn = time.perf_counter()
-            lat[j] = tn - tp    # posterior-to-posterior period of the streaming loop (host clock)
-            tp = tn
+        if pipelined:
+            ses.scan_step_begin(f, sts2[0], Ps2[0], True)
+            if K > 1:
+                ses.scan_prefetch_ptr(pptr[1], pn[1], 16)
+            for j in range(K):
+                if j + 1 < K:
+                    ses.scan_step_begin(f, sts2[j + 1], Ps2[j + 1], True)     # adopts the prefetched scan j+1
+                res2[j] = ses.scan_step_finish(f, sts2[j], Ps2[j])            # scan j done: its buffer is free again
+                if j + 2 < K:
+                    ses.scan_prefetch_ptr(pptr[j + 2], pn[j + 2], 16)
+                tn = time.perf_counter()
+                lat[j] = tn - tp
+                tp = tn
+        else:
+            for j in range(K):
+                ses.scan_step_begin(f, sts2[j], Ps2[j], True)
+                if j + 1 < K:
+                    ses.scan_prefetch_ptr(pptr[j + 1], pn[j + 1], 16)
+                res2[j] = ses.scan_step_finish(f, sts2[j], Ps2[j])
+                tn = time.perf_counter()
+                lat[j] = tn - tp    # posterior-to-posterior period of the streaming loop (host clock)
+                tp = tn
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
@@ -493,6 +520,14 @@ def run_b200(args):
     e2e_ms = float(np.median(e2e_ms_blocks))
     lat = np.concatenate([b[1] for b in eblocks])
     passes = sum(b[2] for b in eblocks) / len(eblocks)
+    # the strictly alternating begin / finish figures (a live filter, whose next prior needs this posterior), one cycle each
+    w, _ = begin_cycle(False)
+    seq_blocks = [timed_block(idx, pipelined=False) for idx in cycle_blocks(w)]
+    w, _ = begin_cycle(False)
+    seq_eblocks = [e2e_block(idx, pipelined=False) for idx in cycle_blocks(w)]
+    seq_ms = float(np.median(dist_max([b[0] for b in seq_blocks], device=devname)))
+    seq_e2e_ms = float(np.median(dist_max([b[0] for b in seq_eblocks], device=devname)))
+    seq_lat = np.concatenate([b[1] for b in seq_eblocks])
     clk = clocks.stop(row_lo, row_hi)
     # per-rank view of the same measurement: own median block time, own GPU's clocks, own e2e
     mine = [float(np.median([b[0] for b in blocks])), float(np.min([b[0] for b in blocks])), float(np.max([b[0] for b in blocks])),
@@ -539,6 +574,11 @@ def run_b200(args):
                                "map_block_storage_mb": stats["blocks_in_use"] * 1024 / 1e6, "pose_err_vs_truth_max_m": perr},
             "timing": {"what": f"{len(blocks)} blocks of exactly {K} steps, each between barrier+synchronize, CUDA events on the "
                                "library stream, max over ranks per block; value = median block",
+                       "pipeline": "two steps in flight (flb_scan_step_begin of scan j+1 before flb_scan_step_finish of scan j: replay, the "
+                                   "priors are known); `sequential` = strictly alternating begin / finish",
+                       "sequential": {"value": aggregate_scans_per_s(world_size, K, seq_ms), "e2e": aggregate_scans_per_s(world_size, K, seq_e2e_ms),
+                                      "blocks": len(seq_blocks), "latency_ms_p50": float(np.percentile(seq_lat, 50) * 1e3),
+                                      "latency_ms_p99": float(np.percentile(seq_lat, 99) * 1e3)},
                        "blocks": len(blocks), "block_ms_median": ms, "block_ms_min": float(ms_blocks.min()),
                        "block_ms_max": float(ms_blocks.max()), "device_ms_total": float(ms_blocks.sum()),
                        "block_ms": [round(float(x), 4) for x in ms_blocks], "blocks_per_cycle": blocks_per_cycle,

@@ -324,23 +324,56 @@ __device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double*
 }  // namespace dev
 
 // Load the propagated state / covariance for a new scan.
-// staging layout: x0[26] | P0[529] | n | flg_EKF_inited   (all doubles, so one H2D copy carries a scan's inputs)
+// staging layout: x0[26] | P0[529] | n | flg_EKF_inited | bits of the device pointer to the scan   (all 8-byte slots).  `stage`
+// is MAPPED PINNED HOST memory: the block reads the scan's inputs straight over PCIe (4.5 KB), no copy node in the graph.
 __global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage, int* work_counts) {
   pdl_sync();
   FLB_TRACE_BEGIN(0);
-  const double* x0 = stage;
-  const double* P0 = stage + 26;
-  const int n = (int)stage[26 + NDOF * NDOF];
+  // the record is 558 doubles: every thread issues its (at most two) 16-byte reads at once — reads of host memory are slow
+  // per request, so few wide requests all in flight
+  __shared__ double sst[26 + NDOF * NDOF + 4];
+  constexpr int NPAIR = (26 + NDOF * NDOF + 4) / 2;
+  const double2* st2 = reinterpret_cast<const double2*>(stage);
+  for (int i = threadIdx.x; i < NPAIR; i += blockDim.x) {
+    const double2 v = st2[i];
+    sst[2 * i] = v.x;
+    sst[2 * i + 1] = v.y;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 48) work_counts[threadIdx.x - 32] = 0;   // per-pass k-NN work-list counters [0..7] + tickets [8..15]
+  __syncthreads();
+  const double* x0 = sst;
+  const double* P0 = sst + 26;
+  const int n = (int)sst[26 + NDOF * NDOF];
   for (int i = threadIdx.x; i < NDOF * NDOF; i += blockDim.x) { c->Pp[i] = P0[i]; c->P[i] = P0[i]; }
   if (threadIdx.x < 26) { c->x[threadIdx.x] = x0[threadIdx.x]; c->xp[threadIdx.x] = x0[threadIdx.x]; }
-  if (threadIdx.x >= 32 && threadIdx.x < 48) work_counts[threadIdx.x - 32] = 0;   // per-pass k-NN work-list counters [0..7] + tickets [8..15]
   __syncthreads();
   if (threadIdx.x == 0) {
     c->it = -1; c->t = 0; c->converge = 1; c->finished = 0; c->need_host = 0; c->passes = 0; c->searches = 0;
-    c->lastM = 0; c->last_res = 0.0; c->n = n; c->flg_inited = (int)stage[26 + NDOF * NDOF + 1];
+    c->lastM = 0; c->last_res = 0.0; c->n = n; c->flg_inited = (int)sst[26 + NDOF * NDOF + 1];
+    c->body = reinterpret_cast<const float4*>((unsigned long long)__double_as_longlong(sst[26 + NDOF * NDOF + 2]));
     dev::pose_from_state(c->x, c->pose);
   }
   FLB_TRACE_END(0);
+}
+
+// Last node of a scan: everything the host reads after a step, written into ONE mapped pinned host record (zero-copy
+// stores over PCIe, ~4.7 KB) — posterior state and covariance, loop statistics, the map counters, map_incremental's counts.
+struct StepResult {
+  double x[26];
+  double P[NDOF * NDOF];
+  double last_res;
+  int passes, searches, lastM, t, need_host, pad_;
+  int counters[32];
+  int cnt2[2];
+};
+__global__ void k_publish(const EsikfCtl* c, const int* __restrict__ counters, const int* __restrict__ cnt2, StepResult* out) {
+  pdl_sync();
+  const int tid = threadIdx.x;
+  for (int i = tid; i < NDOF * NDOF; i += blockDim.x) out->P[i] = c->P[i];
+  if (tid < 26) out->x[tid] = c->x[tid];
+  if (tid >= 32 && tid < 64) out->counters[tid - 32] = counters[tid - 32];
+  if (tid == 64) { out->last_res = c->last_res; out->passes = c->passes; out->searches = c->searches; out->lastM = c->lastM; out->t = c->t; out->need_host = c->need_host; }
+  if (tid == 65) { out->cnt2[0] = cnt2 ? cnt2[0] : 0; out->cnt2[1] = cnt2 ? cnt2[1] : 0; }
 }
 
 // One loop iteration of update_iterated_dyn_share_modified is split in two kernels so that the half that only needs

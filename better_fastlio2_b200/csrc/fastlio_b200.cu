@@ -803,6 +803,7 @@ struct flb_session {
   flb_session_config cfg{};
   int cap = 0, n = 0;
   float4 *body = nullptr, *world = nullptr, *nbr = nullptr, *normvec = nullptr, *plane = nullptr;
+  const float4* body_cur = nullptr;   // the current scan: `body` (uploads, front end) or the caller's device buffer (flb_scan_set_device)
   unsigned char *cnt = nullptr, *sel = nullptr, *cls = nullptr;
   double *partial = nullptr, *dout = nullptr;
   int* offs = nullptr;
@@ -822,16 +823,17 @@ struct flb_session {
   size_t raw_cap = 0;
   // device-driven update
   EsikfCtl* ctl = nullptr;       // device
-  EsikfCtl* h_ctl = nullptr;     // pinned mirror
-  double* d_x0P0 = nullptr;      // device staging of the propagated state (26) + covariance (529)
-  double* h_x0P0 = nullptr;      // pinned
+  EsikfCtl* h_ctl = nullptr;     // pinned scratch (initial upload of ctl)
+  double* h_x0P0 = nullptr;      // working: MAPPED pinned staging of a scan's inputs (k_esikf_begin reads it over PCIe)
+  double* d_x0P0 = nullptr;      //          its device-side address
+  StepResult* h_res = nullptr;   // working: MAPPED pinned result record written by k_publish
+  StepResult* d_res = nullptr;   //          its device-side address
   bool device_update = true;
   EsikfScratch* d_scr = nullptr;
   cudaStream_t side = nullptr;   // second stream: k_esikf_pre overlaps the measurement kernels of the same pass
   cudaEvent_t ev_fork[8] = {nullptr}, ev_join[8] = {nullptr};
-  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [0] update only, [1] update + map_incremental
-  cudaGraphExec_t graph_alt[2] = {nullptr, nullptr};  // the same sequences captured for the other body buffer
-  int graph_kernels[2] = {0, 0}, graph_kernels_alt[2] = {0, 0};
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [0] update only, [1] update + map_incremental (no scan or host pointer baked in
+  int graph_kernels[2] = {0, 0};                  //  beyond the slot's own staging / result records)
   int graph_gen = -1;            // flb_map::gen the graphs were captured at
   // FLB_HOST_TIMING=1: where the host side of a step goes (printed when the session is destroyed)
   bool host_timing = false;
@@ -849,9 +851,45 @@ struct flb_session {
   // flb_scan_step_begin / _finish
   bool step_pending = false, step_device = false;
   bool flags_clean = false;      // sel / cnt hold their per-scan initial values (see scan_reset)
-  int step_l0 = 0, step_deleted = 0, step_flg = 1;
+  int step_l0 = 0, step_deleted = 0, step_flg = 1, step_n = 0;
   double step_x[26], step_P[NDOF * NDOF];
+  // Up to TWO steps may be in flight (begin, begin, finish, begin, finish, ...): everything of a step that lives on the host —
+  // pinned input / result buffers, the graphs whose copy nodes point at them, timing events, the bookkeeping above — exists
+  // once per slot; the members above are the WORKING set = a copy of slot[active] (use_slot switches).  Device buffers are
+  // shared: the steps execute one after the other on the map's stream.
+  struct StepSlot {
+    double *h_x0P0 = nullptr, *d_x0P0 = nullptr;
+    StepResult *h_res = nullptr, *d_res = nullptr;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    int gk[2] = {0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    bool pending = false, device = false;
+    int l0 = 0, deleted = 0, flg = 1, n = 0;
+    double x[26], P[NDOF * NDOF];
+  } slot[2];
+  int active = 0, head = 0, npending = 0;
 };
+
+// working set <-> slots
+static void save_active(flb_session* s) {
+  flb_session::StepSlot& o = s->slot[s->active];
+  for (int i = 0; i < 2; ++i) { o.graph[i] = s->graph[i]; o.gk[i] = s->graph_kernels[i]; }
+  o.pending = s->step_pending; o.device = s->step_device; o.l0 = s->step_l0; o.deleted = s->step_deleted; o.flg = s->step_flg; o.n = s->step_n;
+  memcpy(o.x, s->step_x, sizeof(o.x));
+  memcpy(o.P, s->step_P, sizeof(o.P));
+}
+static void use_slot(flb_session* s, int j) {
+  if (j == s->active) return;
+  save_active(s);
+  const flb_session::StepSlot& w = s->slot[j];
+  s->h_x0P0 = w.h_x0P0; s->d_x0P0 = w.d_x0P0; s->h_res = w.h_res; s->d_res = w.d_res;
+  for (int i = 0; i < 2; ++i) { s->graph[i] = w.graph[i]; s->graph_kernels[i] = w.gk[i]; }
+  s->ev0 = w.ev0; s->ev1 = w.ev1; s->ev2 = w.ev2; s->ev3 = w.ev3;
+  s->step_pending = w.pending; s->step_device = w.device; s->step_l0 = w.l0; s->step_deleted = w.deleted; s->step_flg = w.flg; s->step_n = w.n;
+  memcpy(s->step_x, w.x, sizeof(w.x));
+  memcpy(s->step_P, w.P, sizeof(w.P));
+  s->active = j;
+}
 
 extern "C" void flb_session_default_config(flb_session_config* c) {
   if (!c) return;
@@ -893,11 +931,9 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   A((void**)&s->selint, sizeof(int) * N);
   A((void**)&s->d_cnt2, sizeof(int) * 8);
   A((void**)&s->ctl, sizeof(EsikfCtl));
-  A((void**)&s->d_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
   A((void**)&s->d_scr, sizeof(EsikfScratch));
   if (e == cudaSuccess) e = cudaMemset(s->d_cnt2, 0, sizeof(int) * 8);   // [0..1] map_incremental counts
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_ctl, sizeof(EsikfCtl));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
@@ -926,6 +962,24 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
     s->h_ctl->finished = 1;
     e = cudaMemcpy(s->ctl, s->h_ctl, sizeof(EsikfCtl), cudaMemcpyHostToDevice);
   }
+  // per-step host records (two slots: two steps may be in flight): mapped pinned staging + result, timing events
+  for (int j = 0; j < 2 && e == cudaSuccess; ++j) {
+    flb_session::StepSlot& w = s->slot[j];
+    e = cudaHostAlloc((void**)&w.h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 4), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&w.d_x0P0, w.h_x0P0, 0);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&w.h_res, sizeof(StepResult), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&w.d_res, w.h_res, 0);
+    if (e == cudaSuccess) { memset(w.h_x0P0, 0, sizeof(double) * (26 + NDOF * NDOF + 4)); memset(w.h_res, 0, sizeof(StepResult)); }
+    if (j == 0) { w.ev0 = s->ev0; w.ev1 = s->ev1; w.ev2 = s->ev2; w.ev3 = s->ev3; }
+    else {
+      if (e == cudaSuccess) e = cudaEventCreate(&w.ev0);
+      if (e == cudaSuccess) e = cudaEventCreate(&w.ev1);
+      if (e == cudaSuccess) e = cudaEventCreate(&w.ev2);
+      if (e == cudaSuccess) e = cudaEventCreate(&w.ev3);
+    }
+  }
+  if (e == cudaSuccess) { s->h_x0P0 = s->slot[0].h_x0P0; s->d_x0P0 = s->slot[0].d_x0P0; s->h_res = s->slot[0].h_res; s->d_res = s->slot[0].d_res; }
+  s->body_cur = s->body;
   if (e != cudaSuccess) { flb_session_destroy(s); return set_err("flb_session_create: %s", cudaGetErrorString(e)); }
   if (const char* ht = getenv("FLB_HOST_TIMING")) s->host_timing = atoi(ht) != 0;
   *out = s;
@@ -942,19 +996,25 @@ extern "C" void flb_session_destroy(flb_session* s) {
   Q(cudaStreamSynchronize(s->map->stream));
   if (s->side) Q(cudaStreamSynchronize(s->side));
   if (s->copy_stream) Q(cudaStreamSynchronize(s->copy_stream));
-  for (int i = 0; i < 2; ++i) {
-    if (s->graph[i]) Q(cudaGraphExecDestroy(s->graph[i]));
-    if (s->graph_alt[i]) Q(cudaGraphExecDestroy(s->graph_alt[i]));
-  }
+  save_active(s);
+  for (int j = 0; j < 2; ++j)
+    for (int i = 0; i < 2; ++i)
+      if (s->slot[j].graph[i]) Q(cudaGraphExecDestroy(s->slot[j].graph[i]));
   void* ptrs[] = {s->body, s->body_alt, s->world, s->nbr, s->normvec, s->plane, s->cnt, s->sel, s->cls, s->partial, s->dout, s->offs, s->selint,
-                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->raw_alt, s->ctl, s->d_x0P0, s->d_scr};
+                  s->cub_tmp, s->drows, s->d_cnt2, s->raw, s->raw_alt, s->ctl, s->d_scr};
   for (void* p : ptrs) if (p) Q(cudaFree(p));
   if (s->h_out) Q(cudaFreeHost(s->h_out));
   if (s->h_cnt2) Q(cudaFreeHost(s->h_cnt2));
   if (s->h_ctl) Q(cudaFreeHost(s->h_ctl));
-  if (s->h_x0P0) Q(cudaFreeHost(s->h_x0P0));
-  cudaEvent_t evs[] = {s->ev0, s->ev1, s->ev2, s->ev3, s->ev_copy};
-  for (cudaEvent_t e : evs) if (e) Q(cudaEventDestroy(e));
+  if (!s->slot[0].ev0) { s->slot[0].ev0 = s->ev0; s->slot[0].ev1 = s->ev1; s->slot[0].ev2 = s->ev2; s->slot[0].ev3 = s->ev3; }   // creation failed early
+  for (int j = 0; j < 2; ++j) {
+    flb_session::StepSlot& w = s->slot[j];
+    if (w.h_x0P0) Q(cudaFreeHost(w.h_x0P0));
+    if (w.h_res) Q(cudaFreeHost(w.h_res));
+    cudaEvent_t ev[] = {w.ev0, w.ev1, w.ev2, w.ev3};
+    for (cudaEvent_t e : ev) if (e) Q(cudaEventDestroy(e));
+  }
+  if (s->ev_copy) Q(cudaEventDestroy(s->ev_copy));
   for (int i = 0; i < 8; ++i) { if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i])); if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i])); }
   if (s->side) Q(cudaStreamDestroy(s->side));
   if (s->copy_stream) Q(cudaStreamDestroy(s->copy_stream));
@@ -984,6 +1044,7 @@ static int scan_flags_reset(flb_session* s) {
 }
 static int scan_reset(flb_session* s, int n) {
   s->n = n;
+  s->body_cur = s->body;
   s->have_pass = false;
   s->flags_clean = false;
   // The device-driven sequence always starts with a search pass (esekfom.hpp:1636: converge = true), which rewrites cnt
@@ -1058,19 +1119,19 @@ static int adopt_prefetched(flb_session* s) {
   std::swap(s->body, s->body_alt);
   const int n = s->pending_n;
   s->pending_n = -1;
-  // the captured graphs hold the old body pointer: they are keyed on it
-  for (int i = 0; i < 2; ++i) std::swap(s->graph[i], s->graph_alt[i]);
-  std::swap(s->graph_kernels[0], s->graph_kernels_alt[0]);
-  std::swap(s->graph_kernels[1], s->graph_kernels_alt[1]);
   return scan_reset(s, n);
 }
 
 extern "C" int flb_scan_set_device(flb_session* s, const void* body4_dev, int n) {
   if (!s) return set_err("null session");
   if (n < 0 || n > s->cap) return set_err("scan of %d points exceeds max_scan_points=%d", n, s->cap);
+  if (n > 0 && !body4_dev) return set_err("null device buffer");
   CU(cudaSetDevice(s->map->cfg.device));
-  if (n > 0) CU(cudaMemcpyAsync(s->body, body4_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, s->map->stream));
-  return scan_reset(s, n);
+  // no copy: the scan is read in place (the pointer travels with the staged inputs of the step).  The buffer must stay
+  // valid and unmodified until the last call that works on this scan has returned (flb_scan_step_finish / flb_map_incremental).
+  if (scan_reset(s, n)) return 1;
+  if (n > 0) s->body_cur = static_cast<const float4*>(body4_dev);
+  return 0;
 }
 
 static PoseDev pose_from(const double* st) {
@@ -1082,7 +1143,7 @@ static PoseDev pose_from(const double* st) {
 
 static MeasArgs meas_args(flb_session* s, const PoseDev& pose, int search) {
   MeasArgs a;
-  a.pose = pose; a.body = s->body; a.world = s->world; a.nbr = s->nbr; a.cnt = s->cnt; a.sel = s->sel;
+  a.pose = pose; a.body = s->body_cur; a.world = s->world; a.nbr = s->nbr; a.cnt = s->cnt; a.sel = s->sel;
   a.normvec = s->normvec; a.plane = s->plane; a.partial = s->partial; a.n = s->n; a.search = search;
   a.ctl = nullptr; a.world_out = s->world; a.stride = s->cap;
   return a;
@@ -1097,7 +1158,7 @@ static int enqueue_pass(flb_session* s, const double* state26, int search) {
   s->last_pose = pose;
   {
     ProfScope ps(m, FLB_K_TRANSFORM);
-    k_transform<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body, s->world, n);
+    k_transform<<<grid_for(n, 256, m->sm_count * 8), 256, 0, st>>>(pose, s->body_cur, s->world, n);
     m->launches++;
   }
   if (search) {
@@ -1253,8 +1314,7 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
   const bool overlap = !m->prof_on;  // per-class event timing needs a single in-order stream
   const bool md12 = s->cfg.extrinsic_est_en != 0;   // measured subspace: 12 columns with extrinsic estimation, else 6
   const int cap = s->cap;
-  CU(cudaMemcpyAsync(s->d_x0P0, s->h_x0P0, sizeof(double) * (26 + NDOF * NDOF + 2), cudaMemcpyHostToDevice, st));
-  launch_k(k_esikf_begin, 1, 256, 0, st, s->ctl, (const double*)s->d_x0P0, m->d_misc + 16);
+  launch_k(k_esikf_begin, 1, 256, 0, st, s->ctl, (const double*)s->d_x0P0, m->d_misc + 16);   // reads the mapped pinned staging record
   m->launches++;
   for (int p = 0; p <= s->cfg.max_iterations; ++p) {
     if (overlap) {
@@ -1284,7 +1344,7 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
       KnnArgs a;
       a.m = m->d; a.q = nullptr; a.n = cap; a.nbr = s->nbr; a.cnt = s->cnt; a.max_d2 = INFINITY;
       a.phase_stats = m->prof_on ? m->d_phase : nullptr;
-      a.ctl = s->ctl; a.body = s->body; a.stride = cap; a.work_count = p < 8 ? m->d_misc + 16 + p : nullptr; a.work_ticket = p < 8 ? m->d_misc + 24 + p : nullptr;
+      a.ctl = s->ctl; a.body = nullptr; a.stride = cap; a.work_count = p < 8 ? m->d_misc + 16 + p : nullptr; a.work_ticket = p < 8 ? m->d_misc + 24 + p : nullptr;
       if (launch_knn<5>(m, a)) return 1;
     }
     {
@@ -1305,8 +1365,10 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
   }
   CU(cudaGetLastError());
   if (with_insert && enqueue_map_incremental(s, nullptr, 0, true)) return 1;
-  CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(EsikfCtl), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(m->h_counters, m->d.counters, sizeof(int) * CNT_COUNT, cudaMemcpyDeviceToHost, st));
+  // results: one kernel writes the mapped pinned record (posterior, statistics, map counters, map_incremental's counts)
+  launch_k(k_publish, 1, 256, 0, st, (const EsikfCtl*)s->ctl, (const int*)m->d.counters, (const int*)(with_insert ? s->d_cnt2 : nullptr), s->d_res);
+  m->launches++;
+  CU(cudaGetLastError());
   s->have_pass = false;
   return 0;
 }
@@ -1318,14 +1380,20 @@ static int launch_scan_device(flb_session* s, const double* state26, const doubl
   memcpy(s->h_x0P0 + 26, P, sizeof(double) * NDOF * NDOF);
   s->h_x0P0[26 + NDOF * NDOF] = (double)s->n;
   s->h_x0P0[26 + NDOF * NDOF + 1] = (double)flg_EKF_inited;
+  {
+    const unsigned long long bits = (unsigned long long)reinterpret_cast<uintptr_t>(s->body_cur);
+    memcpy(&s->h_x0P0[26 + NDOF * NDOF + 2], &bits, sizeof(bits));
+  }
   const int gi = with_insert ? 1 : 0;
   if (!s->use_graph || m->prof_on) return enqueue_scan_device(s, with_insert);
   if (s->graph_gen != m->gen) {
     // a buffer baked into the captured sequences was reallocated (or the voxel size changed) since: capture again
+    flb_session::StepSlot& o = s->slot[1 - s->active];
     for (int i = 0; i < 2; ++i) {
       if (s->graph[i]) { Q(cudaGraphExecDestroy(s->graph[i])); s->graph[i] = nullptr; }
-      if (s->graph_alt[i]) { Q(cudaGraphExecDestroy(s->graph_alt[i])); s->graph_alt[i] = nullptr; }
+      if (o.graph[i]) { Q(cudaGraphExecDestroy(o.graph[i])); o.graph[i] = nullptr; }
     }
+    s->graph_gen = m->gen;   // (both slots start over: graphs are re-captured lazily, the first capture stamps this again)
   }
   if (!s->graph[gi]) {
     // everything the captured sequence may allocate lazily must exist before capture
@@ -1367,12 +1435,13 @@ static int launch_scan_device(flb_session* s, const double* state26, const doubl
   m->launches += s->graph_kernels[gi];
   return 0;
 }
-static int finish_counters(flb_map* m) {  // after the stream drained: interpret the counters copied by the sequence
+static int finish_counters(flb_map* m, const int* snapshot) {  // after the sequence completed: interpret the counters it copied
+  memcpy(m->h_counters, snapshot, sizeof(int) * CNT_COUNT);
   const int e = absorb_range_flag(m);
   if (e) return set_err("device map error flags 0x%x (capacity exceeded or point out of range; see flb_map_get_stats)", e);
   return 0;
 }
-static void stats_from_ctl(const EsikfCtl* c, flb_update_stats* stats) {
+static void stats_from_ctl(const StepResult* c, flb_update_stats* stats) {
   if (!stats) return;
   stats->passes = c->passes; stats->search_passes = c->searches; stats->effct_feat_num = c->lastM;
   stats->converged_count = c->t; stats->total_residual = c->last_res;
@@ -1380,6 +1449,7 @@ static void stats_from_ctl(const EsikfCtl* c, flb_update_stats* stats) {
 
 extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_update_stats* stats) {
   if (!s || !state26 || !P) return set_err("flb_esikf_update: null argument");
+  if (s->npending) return set_err("flb_esikf_update: a flb_scan_step is in flight");
   CU(cudaSetDevice(s->map->cfg.device));
   if (adopt_prefetched(s)) return 1;
   if (!s->device_update) return run_update(s, state26, P, stats);
@@ -1388,11 +1458,11 @@ extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_
   if (launch_scan_device(s, state26, P, 1, false)) return 1;
   CU(cudaEventRecord(s->ev1, m->stream));
   CU(cudaStreamSynchronize(m->stream));
-  if (finish_counters(m)) return 1;
-  if (s->h_ctl->need_host) return run_update(s, state26, P, stats);  // M < 23: explicit-row branch on the host
-  memcpy(state26, s->h_ctl->x, sizeof(double) * 26);
-  memcpy(P, s->h_ctl->P, sizeof(double) * NDOF * NDOF);
-  stats_from_ctl(s->h_ctl, stats);
+  if (finish_counters(m, s->h_res->counters)) return 1;
+  if (s->h_res->need_host) return run_update(s, state26, P, stats);  // M < 23: explicit-row branch on the host
+  memcpy(state26, s->h_res->x, sizeof(double) * 26);
+  memcpy(P, s->h_res->P, sizeof(double) * NDOF * NDOF);
+  stats_from_ctl(s->h_res, stats);
   if (stats) CU(cudaEventElapsedTime(&stats->gpu_ms, s->ev0, s->ev1));
   return 0;
 }
@@ -1416,7 +1486,7 @@ static int enqueue_map_incremental(flb_session* s, const double* state26, int fl
   {
     ProfScope ps(m, FLB_K_CLASSIFY);
     launch_k(k_classify, grid_for(npts, 256, m->sm_count * 8), 256, 0, st, pose, (const EsikfCtl*)(from_ctl ? s->ctl : nullptr),
-             (const float4*)s->body, (const float4*)s->nbr, (const unsigned char*)s->cnt, n, s->cap, flg_EKF_inited, s->cfg.filter_size_map_min,
+             (const float4*)s->body_cur, (const float4*)s->nbr, (const unsigned char*)s->cnt, n, s->cap, flg_EKF_inited, s->cfg.filter_size_map_min,
              s->world, s->cls, s->d_cnt2, m->d, m->skeys, m->sbest, sc - 1);
     m->launches++;
   }
@@ -1424,7 +1494,7 @@ static int enqueue_map_incremental(flb_session* s, const double* state26, int fl
   if (from_ctl) {
     if (insert_device(m, s->world, s->cls, s->cap, 2, &s->ctl->need_host, &s->ctl->n, true)) return 1;
   } else if (insert_device(m, s->world, s->cls, n, 2, nullptr, nullptr, true)) return 1;
-  CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  if (!from_ctl) CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));   // (k_publish carries them otherwise)
   return 0;
 }
 
@@ -1542,7 +1612,10 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
                                    const double* P, int flg_EKF_inited) {
   if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
   flb_map* m = s->map;
-  if (s->step_pending) return set_err("flb_scan_step_begin: the previous step has not been collected (call flb_scan_step_finish first)");
+  if (s->npending >= 2) return set_err("flb_scan_step_begin: two steps are already in flight (call flb_scan_step_finish first)");
+  if (s->npending == 1 && !s->device_update)
+    return set_err("flb_scan_step_begin: the host-driven engine runs one step at a time (call flb_scan_step_finish first)");
+  use_slot(s, (s->head + s->npending) & 1);
   const auto ht0 = std::chrono::steady_clock::now();
   if (s->host_timing && s->ht_n > 0) s->ht_between += std::chrono::duration<double>(ht0 - s->ht_last_finish).count();
   CU(cudaSetDevice(m->cfg.device));
@@ -1567,34 +1640,46 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
     CU(cudaEventRecord(s->ev1, m->stream));
     CU(cudaEventRecord(s->ev3, m->stream));
   }
+  s->step_n = s->n;
+  s->step_l0 = m->launches - s->step_l0;   // kernels launched by this step so far (a younger step may add its own before finish)
   s->step_pending = true;
+  s->npending++;
   if (s->host_timing) s->ht_begin += std::chrono::duration<double>(std::chrono::steady_clock::now() - ht0).count();
   return 0;
 }
 
 extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* state26, double* P, flb_scan_result* out) {
   if (!s || !state26 || !P) return set_err("flb_scan_step: null argument");
-  if (!s->step_pending) return set_err("flb_scan_step_finish without flb_scan_step_begin");
+  if (s->npending == 0) return set_err("flb_scan_step_finish without flb_scan_step_begin");
+  use_slot(s, s->head);          // the OLDEST step in flight
   s->step_pending = false;
+  s->head ^= 1;
+  s->npending--;
   flb_map* m = s->map;
   CU(cudaSetDevice(m->cfg.device));
   flb_scan_result r;
   memset(&r, 0, sizeof(r));
   r.n_deleted = s->step_deleted;
   bool host_path = !s->step_device;
+  const int launches0 = m->launches;
   const auto hf0 = std::chrono::steady_clock::now();
   auto hf1 = hf0;
   if (!host_path) {
-    CU(cudaStreamSynchronize(m->stream));                  // the single synchronisation of the step
+    CU(cudaEventSynchronize(s->ev3));                      // the single synchronisation of the step (a younger step may be running on)
     hf1 = std::chrono::steady_clock::now();
-    if (finish_counters(m)) return 1;
+    if (finish_counters(m, s->h_res->counters)) return 1;
     m->has_root = m->has_root || m->h_counters[CNT_VALID] > 0;
-    if (s->h_ctl->need_host) {
+    if (s->h_res->need_host) {
+      if (s->npending)
+        return set_err("flb_scan_step_finish: under-determined scan (fewer than 23 rows) while a younger step is already in flight; "
+                       "such scans need the host-driven branch: run them with strictly alternating begin / finish");
       host_path = true;                                    // M < 23 branch: redo this scan on the host-driven path
     } else {
-      memcpy(state26, s->h_ctl->x, sizeof(double) * 26);
-      memcpy(P, s->h_ctl->P, sizeof(double) * NDOF * NDOF);
-      stats_from_ctl(s->h_ctl, &r.update);
+      memcpy(state26, s->h_res->x, sizeof(double) * 26);
+      memcpy(P, s->h_res->P, sizeof(double) * NDOF * NDOF);
+      stats_from_ctl(s->h_res, &r.update);
+      s->h_cnt2[0] = s->h_res->cnt2[0];
+      s->h_cnt2[1] = s->h_res->cnt2[1];
       CU(cudaEventElapsedTime(&r.update.gpu_ms, s->ev0, s->ev1));
     }
   }
@@ -1602,7 +1687,7 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
     memcpy(state26, s->step_x, sizeof(s->step_x));
     memcpy(P, s->step_P, sizeof(s->step_P));
     if (run_update(s, state26, P, &r.update)) return 1;  // :2380
-    if (s->n > 0 && enqueue_map_incremental(s, state26, s->step_flg, false)) return 1;  // :2401
+    if (s->step_n > 0 && enqueue_map_incremental(s, state26, s->step_flg, false)) return 1;  // :2401
     CU(cudaEventRecord(s->ev3, m->stream));
     if (fetch_counters(m)) return 1;
   }
@@ -1611,11 +1696,11 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
     host::V3 pl = x.pos + host::rotate(x.rot, x.offT);
     for (int i = 0; i < 3; ++i) fov->pos_lid[i] = pl.a[i];
   }
-  r.n_to_add = s->n > 0 ? s->h_cnt2[0] : 0;
-  r.n_no_downsample = s->n > 0 ? s->h_cnt2[1] : 0;
+  r.n_to_add = s->step_n > 0 ? s->h_cnt2[0] : 0;
+  r.n_no_downsample = s->step_n > 0 ? s->h_cnt2[1] : 0;
   r.map_valid = m->h_counters[CNT_VALID];
   CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
-  r.kernel_launches = m->launches - s->step_l0;
+  r.kernel_launches = s->step_l0 + (m->launches - launches0);
   if (out) *out = r;
   const int rrc = maybe_rehash(m);
   if (s->host_timing) {

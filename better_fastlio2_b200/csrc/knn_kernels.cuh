@@ -169,6 +169,7 @@ struct EsikfCtl {
   int max_iter, it, t, converge, finished, need_host, passes, searches, lastM, n;
   int flg_inited;      // flg_EKF_inited of this scan (laserMapping.cpp:2317)
   int pad_;
+  const float4* body;  // feats_down_body of this scan (travels with the staged inputs: the captured graphs do not depend on it)
 };
 __device__ __forceinline__ bool ctl_pass_active(const EsikfCtl* c) { return !c->finished && c->it < c->max_iter; }
 
@@ -183,8 +184,8 @@ struct KnnArgs {
   int* worklist;       // stencil kernel: indices of queries it could not prove complete; warp kernel: its input list
   int* work_count;     // number of entries in worklist (device)
   int* work_ticket;    // exact kernel: next unclaimed work-list entry (device, zeroed with work_count)
-  const EsikfCtl* ctl; // device-driven mode: queries = body_to_world(ctl->pose, body[i]); skipped unless a search pass
-  const float4* body;
+  const EsikfCtl* ctl; // device-driven mode: queries = body_to_world(ctl->pose, ctl->body[i]); skipped unless a search pass
+  const float4* body;  // (unused: the scan pointer of the device-driven mode is ctl->body)
   int stride;          // leading dimension of nbr (>= n; the session capacity, so launches do not depend on n)
 };
 
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
   for (;; ) {
     if (w >= nwork) break;   // warp-uniform
     const int i = a.worklist[w];
-    const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
+    const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.ctl->body[i])) : __ldg(&a.q[i]);
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     TopK<K> t;
     t.clear();
@@ -829,7 +830,7 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
   if (i >= (a.ctl ? a.ctl->n : a.n)) return;
   const float ds = m.ds;
   const float lim = a.max_d2;
-  const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.body[i])) : __ldg(&a.q[i]);
+  const float4 q4 = a.ctl ? body_to_world(a.ctl->pose, __ldg(&a.ctl->body[i])) : __ldg(&a.q[i]);
   const float qx = q4.x, qy = q4.y, qz = q4.z;
   const float qlim = 4.0e6f * ds;
   TopKId<K> t;

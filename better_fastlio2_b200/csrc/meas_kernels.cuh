@@ -251,7 +251,7 @@ __device__ __forceinline__ bool select_point(const MeasArgs& a, int i, int searc
     const float4 pl = a.plane[i];
     pa = pl.x; pb_ = pl.y; pc = pl.z; pd = pl.w;
   }
-  const float4 pb = a.body[i];
+  const float4 pb = (a.ctl ? a.ctl->body : a.body)[i];
   const float pd2 = pa * pw.x + pb_ * pw.y + pc * pw.z + pd;  // :1925 (float, left to right)
   const double bn = sqrt((double)pb.x * (double)pb.x + (double)pb.y * (double)pb.y + (double)pb.z * (double)pb.z);
   const float sc = (float)(1.0 - 0.9 * (double)fabsf(pd2) / sqrt(bn));  // :1927
@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
   FLB_TRACE_BEGIN(4 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !ctl_pass_active(a.ctl)) return;   // the iterated update already finished (block-uniform)
   const PoseDev pose = a.ctl ? a.ctl->pose : a.pose;
+  const float4* __restrict__ body = a.ctl ? a.ctl->body : a.body;
   const int search = a.ctl ? a.ctl->converge : a.search;
   const int n = a.ctl ? a.ctl->n : a.n;
   const int stride = gridDim.x * blockDim.x;
@@ -292,14 +293,14 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
     bool sel = false;
     if (i < n) {
       float4 pw;
-      if (a.ctl) { pw = body_to_world(pose, a.body[i]); a.world_out[i] = pw; }
+      if (a.ctl) { pw = body_to_world(pose, body[i]); a.world_out[i] = pw; }
       else pw = a.world[i];
       sel = select_point(a, i, search, pw, nv);
       a.sel[i] = sel ? 1 : 0;
       if (sel) a.normvec[i] = nv;
     }
     double row[13];
-    if (sel) jacobian_row<EXTR>(pose, a.body[i], nv, row);
+    if (sel) jacobian_row<EXTR>(pose, body[i], nv, row);
     const unsigned any = __ballot_sync(FULL, sel);
     if (any == 0u) continue;
     if (EXTR) {
@@ -403,7 +404,7 @@ __global__ void k_sel_to_int(const unsigned char* __restrict__ sel, int* __restr
 // Fused with the first two steps of the insert (K3a touch_block: make sure the block of every point to be added exists;
 // K3c scatter: per-voxel best new point of the downsampled class into the scratch hash) when a scratch hash is passed:
 // both only need the point and its class, so the points are read once and two launches disappear from the scan's tail.
-__global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __restrict__ body, const float4* __restrict__ nbr,
+__global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* body, const float4* __restrict__ nbr,
                            const unsigned char* __restrict__ cnt, int n_in, int nbr_stride, int flg_in, double fs,
                            float4* __restrict__ world, unsigned char* __restrict__ cls, int* counts, MapDev m, uint64_t* skeys,
                            unsigned long long* sbest, uint32_t smask) {
@@ -411,6 +412,7 @@ __global__ void k_classify(PoseDev s_in, const EsikfCtl* ctl, const float4* __re
   FLB_TRACE_BEGIN(6 * 8);
   if (ctl && ctl->need_host) return;  // the host fallback redoes update + insert for this scan
   const PoseDev s = ctl ? ctl->pose : s_in;
+  if (ctl) body = ctl->body;
   const int n = ctl ? ctl->n : n_in;
   const int flg_EKF_inited = ctl ? ctl->flg_inited : flg_in;
   const int lane = threadIdx.x & 31;

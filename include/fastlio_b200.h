@@ -154,7 +154,9 @@ int flb_scan_upload_pt(flb_session* s, const void* body_pts, int n, int stride_b
  * becomes current at the next flb_scan_step / flb_esikf_update called with body == NULL (which waits for the copy).
  * body_xyz must stay valid (pinned memory recommended) until then; stride 12 or 16 only. */
 int flb_scan_prefetch(flb_session* s, const float* body_xyz, int n, int stride_bytes);
-/* Same, when the scan already lives in device memory as n float4 (x,y,z,*) on the session's device. */
+/* Same, when the scan already lives in device memory as n float4 (x, y, z, intensity) on the session's device.  The scan is
+ * read IN PLACE (no copy; its address travels with the staged inputs of the step): the buffer must stay valid and unmodified
+ * until the last call working on this scan (flb_scan_step[_finish], flb_esikf_update, flb_map_incremental, flb_pass...) returned. */
 int flb_scan_set_device(flb_session* s, const void* body_xyz4_dev, int n);
 
 typedef struct flb_pass_result {
@@ -228,7 +230,14 @@ int flb_scan_step(flb_session* s, flb_fov_state* fov, const float* body_xyz, int
 
 /* The same step split at its single synchronisation point, for streaming callers:
  *   flb_scan_step_begin(...);  flb_scan_prefetch(next scan);  flb_scan_step_finish(...);
- * overlaps the upload of the next scan with the kernels of this one. */
+ * overlaps the upload of the next scan with the kernels of this one.
+ * Replay / batch callers whose next prior does not depend on this posterior may keep TWO steps in flight
+ *   begin(k); prefetch(k+1); loop { begin(k+1); finish(k); prefetch(k+2); ... }
+ * so that the device never waits for the host between scans (finish always collects the OLDEST step; a third begin is
+ * refused).  Results are identical to alternating calls.  Constraints of the two-deep mode: the device-driven engine only; the
+ * fov segment of step k+1 sees the lidar position of step k-1; a scan with fewer than 23 effective rows (the explicit-row
+ * branch, esekfom.hpp:1720-1750, handled on the host) makes flb_scan_step_finish fail if a younger step is already queued.
+ * A live filter (prior k+1 = IMU propagation of posterior k) alternates begin / finish and is unaffected. */
 int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const float* body_xyz, int n, int stride_bytes,
                         const double* state26, const double* P, int flg_EKF_inited);
 int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* state26, double* P, flb_scan_result* out);

@@ -180,12 +180,13 @@ def test_other_sensor_configs_match_oracle(oracle, model, ds, ext, stride):
 
 
 def test_prefetch_and_split_step_equal_plain_step(oracle):
-    """flb_scan_prefetch + flb_scan_step_begin/_finish (double-buffered upload) == flb_scan_step with a host buffer."""
+    """flb_scan_prefetch + flb_scan_step_begin/_finish (double-buffered upload), alternating or with two steps in flight, ==
+    flb_scan_step with a host buffer (bit for bit: states, covariances, map contents)."""
     import torch
     scs = [small_scene(seed=s, map_half=25.0, half_extent=80.0) for s in (7, 8, 9)]
     mp = scs[0]["map"]
     outs = []
-    for mode in ("plain", "prefetch"):
+    for mode in ("plain", "prefetch", "two_in_flight"):
         t = capi.KDTree(voxel_size=0.2, max_points=1 << 19, max_blocks=1 << 16)
         t.Build(mp)
         ses = capi.Session(t, max_scan_points=40000, max_iterations=3)
@@ -194,6 +195,30 @@ def test_prefetch_and_split_step_equal_plain_step(oracle):
             for sc in scs:
                 s, P, r = ses.scan_step(None, sc["body"], sc["prior"], sc["P"], True)
                 res.append((s, P, r.map_valid))
+        elif mode == "two_in_flight":
+            # replay mode: begin(k+1) before finish(k); finish collects the oldest step; a third begin is refused
+            pins = []
+            for sc in scs:
+                b4 = np.zeros((len(sc["body"]), 4), np.float32)
+                b4[:, :3] = sc["body"]
+                pins.append(torch.from_numpy(b4).pin_memory())
+            sts = [sc["prior"].copy() for sc in scs]
+            Ps = [sc["P"].copy() for sc in scs]
+            ses.scan_prefetch_ptr(pins[0].data_ptr(), len(scs[0]["body"]), 16)
+            ses.scan_step_begin(None, sts[0], Ps[0], True)
+            ses.scan_prefetch_ptr(pins[1].data_ptr(), len(scs[1]["body"]), 16)
+            for i in range(len(scs)):
+                if i + 1 < len(scs):
+                    ses.scan_step_begin(None, sts[i + 1], Ps[i + 1], True)
+                    if i == 0:
+                        with pytest.raises(capi.FlbError, match="two steps are already in flight"):
+                            ses.scan_step_begin(None, sts[2], Ps[2], True)
+                r = ses.scan_step_finish(None, sts[i], Ps[i])
+                if i + 2 < len(scs):
+                    ses.scan_prefetch_ptr(pins[i + 2].data_ptr(), len(scs[i + 2]["body"]), 16)
+                res.append((sts[i], Ps[i], r.map_valid))
+            with pytest.raises(capi.FlbError, match="without flb_scan_step_begin"):
+                ses.scan_step_finish(None, sts[0], Ps[0])
         else:
             pins = []
             for sc in scs:
@@ -212,9 +237,10 @@ def test_prefetch_and_split_step_equal_plain_step(oracle):
         outs.append((res, sort_rows(t.flatten())))
         ses.close()
         t.close()
-    for (s0, P0, v0), (s1, P1, v1) in zip(outs[0][0], outs[1][0]):
-        assert np.array_equal(s0, s1) and np.array_equal(P0, P1) and v0 == v1
-    assert np.array_equal(outs[0][1], outs[1][1])
+    for other in (1, 2):
+        for (s0, P0, v0), (s1, P1, v1) in zip(outs[0][0], outs[other][0]):
+            assert np.array_equal(s0, s1) and np.array_equal(P0, P1) and v0 == v1, other
+        assert np.array_equal(outs[0][1], outs[other][1]), other
 
 
 def test_map_destroyed_before_session_is_safe(scene):
@@ -286,3 +312,53 @@ def test_intensity_travels_with_map_points(scene, oracle):
     ses.close()
     t.close()
     ref.close()
+
+
+def test_scan_set_device_reads_in_place(oracle):
+    """flb_scan_set_device: the scan stays in the caller's device buffer (no copy) — same results as the host upload, also
+    with two steps in flight over two different device buffers, and on the host-driven engine."""
+    import torch
+    scs = [small_scene(seed=s, map_half=25.0, half_extent=80.0) for s in (7, 8, 9)]
+    outs = []
+    for mode in ("host", "device", "device_two_in_flight", "device_host_engine"):
+        t = capi.KDTree(voxel_size=0.2, max_points=1 << 19, max_blocks=1 << 16)
+        t.Build(scs[0]["map"])
+        ses = capi.Session(t, max_scan_points=40000, max_iterations=3)
+        res = []
+        devs = []
+        for sc in scs:
+            b4 = np.zeros((len(sc["body"]), 4), np.float32)
+            b4[:, :3] = sc["body"]
+            devs.append(torch.from_numpy(b4).cuda())
+        torch.cuda.synchronize()
+        if mode == "host":
+            for sc in scs:
+                s, P, r = ses.scan_step(None, sc["body"], sc["prior"], sc["P"], True)
+                res.append((s, P, r.map_valid))
+        elif mode == "device_two_in_flight":
+            sts = [sc["prior"].copy() for sc in scs]
+            Ps = [sc["P"].copy() for sc in scs]
+            ses.scan_set_device(devs[0].data_ptr(), len(scs[0]["body"]))
+            ses.scan_step_begin(None, sts[0], Ps[0], True)
+            for i in range(len(scs)):
+                if i + 1 < len(scs):
+                    ses.scan_set_device(devs[i + 1].data_ptr(), len(scs[i + 1]["body"]))
+                    ses.scan_step_begin(None, sts[i + 1], Ps[i + 1], True)
+                r = ses.scan_step_finish(None, sts[i], Ps[i])
+                res.append((sts[i], Ps[i], r.map_valid))
+        else:
+            ses.set_update_engine(mode == "device")
+            for i, sc in enumerate(scs):
+                st, P = sc["prior"].copy(), sc["P"].copy()
+                ses.scan_set_device(devs[i].data_ptr(), len(sc["body"]))
+                r = ses.scan_step_ptr(None, None, 0, 0, st, P)
+                res.append((st, P, r.map_valid))
+        outs.append((res, sort_rows(t.flatten())))
+        ses.close()
+        t.close()
+    for other in (1, 2):
+        for (s0, P0, v0), (s1, P1, v1) in zip(outs[0][0], outs[other][0]):
+            assert np.array_equal(s0, s1) and np.array_equal(P0, P1) and v0 == v1, other
+        assert np.array_equal(outs[0][1], outs[other][1]), other
+    for (s0, P0, v0), (s1, P1, v1) in zip(outs[0][0], outs[3][0]):     # the host-driven engine agrees to ~1e-13 (other reduction order)
+        assert np.abs(s0 - s1).max() < 1e-9 and abs(v0 - v1) <= 2

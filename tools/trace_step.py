@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--pairs", type=int, default=10, help="also time PAIRS of steps in flight together (inter-step gap)")
     args = ap.parse_args()
     import torch
     from better_fastlio2_b200 import capi
@@ -118,6 +119,29 @@ def main():
             print("# exact kernel, cycles/query by phase: " + ", ".join(
                 f"{nm}={dbg_sum[i] / nq:.0f}" for nm, i in (("ticket+seed loads", 32), ("enumerate+probe", 33), ("compaction push", 34),
                                                             ("point loads+insert", 35), ("merge", 36))))
+    if args.pairs > 0:
+        # two steps in flight: device time from the first kernel of step k to the last kernel of step k+1, against twice the
+        # single-step span -> what the device loses BETWEEN two graph launches (copies, graph start-up)
+        spans = []
+        base = args.warmup
+        for j in range(args.pairs):
+            k0, k1 = base + (2 * j) % args.steps, base + (2 * j + 1) % args.steps
+            sa, Pa = work["priors"][k0].copy(), work["P"].copy()
+            sb, Pb = work["priors"][k1].copy(), work["P"].copy()
+            ses.scan_set_device(dev[k0].data_ptr(), len(work["scans"][k0]))
+            ses.scan_step_begin(fov, sa, Pa, True)
+            ses.scan_set_device(dev[k1].data_ptr(), len(work["scans"][k1]))
+            ses.scan_step_begin(fov, sb, Pb, True)
+            ses.scan_step_finish(fov, sa, Pa)
+            ses.scan_step_finish(fov, sb, Pb)
+            L.flb_debug_trace_read(tr, ph, dbg)
+            t = np.array(tr, dtype=np.uint64).reshape(NS, 2)
+            ok = t[:, 0] != np.uint64(0xFFFFFFFFFFFFFFFF)
+            spans.append((int(t[ok, 1].max()) - int(t[0, 0])) * 1e-3)
+        single = float(np.mean(total))
+        print(f"# two steps in flight: first kernel of step k -> last kernel of step k+1 = {np.mean(spans):.1f} us; 2 x single span = "
+              f"{2 * single:.1f} us; inter-step gap on the device = {np.mean(spans) - 2 * single:.1f} us")
+        out["pair_span_us_mean"] = float(np.mean(spans))
     out["dbg_sum"] = dbg_sum.tolist()
     out["dbg_max"] = dbg_max.tolist()
     if args.out:
