@@ -815,7 +815,7 @@ def main():
         log("note: timing rules ask for >= 3 warm-up steps")
     if args.config != "cfg2":
         import bench_configs
-        return bench_configs.run(args)
+        return bench_configs.run(args, sys.modules[__name__])
     if args.impl == "reference":
         args.steps = min(args.steps, REF_STEPS_CAP)  # bounded sample
         run_reference(args)

@@ -327,24 +327,53 @@ __device__ __noinline__ void warp_finish_coarse(MapDev m, float4* nbr, unsigned 
                                (float)(qcx + 2) * cs32, (float)(qcy + 2) * cs32, (float)(qcz + 2) * cs32, mg);
       const bool wdone = (wcount == K && wthr < cov) || cov > lim;
       if (!wdone) {
-        // ---------------- phase C: exhaustive scan of the coarse hash with box-distance pruning
+        // ---------------- phase C: every other coarse cell of the map, pruned by its box distance.  Nearest first: while the
+        // query has no k-th distance yet (far outside the map: nothing to prune with), the cell(s) at the smallest box distance
+        // not visited so far are scanned and merged — the first one or two give a bound that prunes almost all of the rest —
+        // then one sweep over the remaining cells with that bound.
         phase = 3;
         const int ncs = m.counters[CNT_COARSE_USED];   // dense list of occupied coarse cells
-#pragma unroll 1
-        for (int base = 0; base < ncs; base += 32) {
-          const int li = base + lane;
-          const int cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
+        auto cell_md = [&](int li, int& cs) -> float {   // box distance of list entry li (INF: no cell / inside the 3x3x3 already done)
+          cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
           const uint64_t ck = cs >= 0 ? __ldg(&m.ckeys[cs]) : KEY_EMPTY;
-          bool go = false;
-          if (ck != KEY_EMPTY) {
-            int cx, cy, cz;
-            unpack_key(ck, cx, cy, cz);
-            if (!(abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1)) {
-              const float md = box_mind2(wqx, wqy, wqz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32,
-                                         (float)(cx + 1) * cs32, (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
-              go = (wcount < K || md <= wthr) && md <= lim;
+          if (ck == KEY_EMPTY) return CUDART_INF_F;
+          int cx, cy, cz;
+          unpack_key(ck, cx, cy, cz);
+          if (abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1) return CUDART_INF_F;
+          return box_mind2(wqx, wqy, wqz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32, (float)(cx + 1) * cs32,
+                           (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
+        };
+        float level = -1.f;   // cells with md <= level have been scanned
+#pragma unroll 1
+        for (int iter = 0; iter < 16 && wcount < K; ++iter) {
+          float best = CUDART_INF_F;
+#pragma unroll 1
+          for (int base = 0; base < ncs; base += 32) {
+            int cs;
+            const float md = cell_md(base + lane, cs);
+            if (md > level && md <= lim) best = fminf(best, md);
+          }
+          best = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(best)));   // (non-negative floats order like their bits)
+          if (!(best < CUDART_INF_F)) break;
+#pragma unroll 1
+          for (int base = 0; base < ncs; base += 32) {
+            int cs;
+            const float md = cell_md(base + lane, cs);
+            unsigned todo = __ballot_sync(FULL, md == best);
+            while (todo) {
+              const int c = __ffs(todo) - 1;
+              todo &= todo - 1;
+              scan_coarse_cell<K>(m, __shfl_sync(FULL, cs, c), lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
             }
           }
+          wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
+          level = best;
+        }
+#pragma unroll 1
+        for (int base = 0; base < ncs; base += 32) {
+          int cs;
+          const float md = cell_md(base + lane, cs);
+          const bool go = md > level && md < CUDART_INF_F && (wcount < K || md <= wthr) && md <= lim;
           unsigned todo = __ballot_sync(FULL, go);
           if (!todo) continue;
           while (todo) {
@@ -494,6 +523,8 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
           if (wi < 27 * 8) cb[wi] = cs >= 0 ? __ldg(&m.cbits[(size_t)cs * 8 + (wi & 7)]) : 0ull;
         }
         __syncwarp();
+        // nothing at all within the 3x3x3 coarse cells (a return far outside the map): rings 3..8 cannot find anything
+        if (__ballot_sync(FULL, mycs >= 0) == 0u) break;
       }
       const float bound = fminf(gcount == K ? thr : CUDART_INF_F, lim);
       const int wd = 2 * r + 1;
