@@ -84,13 +84,17 @@ def parity_frames_default():
 SENSOR_HEIGHT = 1.8  # the world origin is the first sensor pose (as in a FAST-LIO run): the ground plane is at z = -1.8 m
 
 
-def make_workload(seed, n_scans, need_map=True, origin_height=SENSOR_HEIGHT):
+def make_workload(seed, n_scans, need_map=True, origin_height=SENSOR_HEIGHT, stream=0):
     """Seeded cfg2 workload: world, map pre-fill (~5M pts), n_scans HDL-64 scans + priors along a 10 m/s trajectory.
 
     origin_height: height of the world origin above the ground plane.  FAST-LIO's world frame is the first IMU pose, so the
     ground lies ~a sensor height BELOW the origin.  (Round 1 generated the ground at z = 0: every ground plane fit of
     esti_plane — it solves A x = -1, common_lib.h:506-536, singular for a plane through the origin — was then ill-conditioned
-    in float32 and the closed loop amplified 1-ulp differences by 1e5 per frame)"""
+    in float32 and the closed loop amplified 1-ulp differences by 1e5 per frame)
+
+    stream: independent realisation of the SAME route (world, pre-filled map, trajectory): its own range noise and priors.  The
+    multi-GPU replicas use stream = rank, so that every GPU does the same amount of work (weak scaling: per-GPU work fixed) on
+    an independent session; stream 0 is the single-GPU workload."""
     from better_fastlio2_b200 import synth
     rng = np.random.default_rng(seed)
     dz = -float(origin_height)
@@ -102,6 +106,8 @@ def make_workload(seed, n_scans, need_map=True, origin_height=SENSOR_HEIGHT):
     xh = 0.5 * n_scans + 105.0
     half = 20.0 if TINY else (xh, max(105.0, MAP_AREA / (4.0 * xh)), 1e3)
     mp = synth.sample_surface_map(world, centre, half, DS, rng, zmax=25.0 + dz) if need_map else None
+    if stream:
+        rng = np.random.default_rng([seed, stream])
     scans, priors, truths = [], [], []
     for k in range(n_scans):
         st = synth.trajectory_state(k, speed=10.0, z=1.8 + dz)
@@ -115,7 +121,7 @@ def make_workload(seed, n_scans, need_map=True, origin_height=SENSOR_HEIGHT):
 def workload_config():
     """The `config` object: identical in both arms (the driver compares them)."""
     return {"workload": "cfg2: HDL-64 120k-ray scans (Q-raw), 0.2 m voxel, ~5M-pt map, max_iteration=3; one independent "
-                        "session per GPU (cfg5 seeds 20+rank)",
+                        "session per GPU (cfg5: the same route and map on every GPU = fixed per-GPU work, own range noise and priors)",
             "seed": SEED, "n_scans": n_scans_default(), "parity_frames": parity_frames_default(),
             "frame_schedule": "cycle 0: frames 0..parity_frames-1 from the fresh map (untimed, checked against the CPU replay), "
                               "then blocks of K consecutive frames; later cycles: map rebuilt (untimed), W warm-up frames, blocks of K",
@@ -352,7 +358,7 @@ def run_b200(args):
     PROF = 10 if not (TINY or NCU_SHORT) else 2  # profiled steps (per-kernel CUDA-event timing) after the timed regions
     NS, F = n_scans_default(), parity_frames_default()
     t_gen = time.perf_counter()
-    work = make_workload(SEED + rank, NS)  # cfg5: independent sessions, seeds 20..27
+    work = make_workload(SEED, NS, stream=rank)  # cfg5: one independent session per GPU (same route, own noise and priors)
     log(f"[rank {rank}] workload: map {len(work['map'])} pts, {NS} scans, gen {time.perf_counter() - t_gen:.1f}s")
     tree = capi.KDTree(voxel_size=DS, max_points=16 << 20, max_blocks=2 << 20, device=local)
     build_map(tree, work["map"])
