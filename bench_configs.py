@@ -88,24 +88,34 @@ def parity_frames(capi, po, synth, work, ds, max_iter, extr, frames, tree, fov_k
 
 
 # --------------------------------------------------------------------------------------------------------------- cfg3
-def run_cfg3(args):
-    import torch
-    from better_fastlio2_b200 import capi, synth
-    DS3, MAXIT, KD_STEP, RADIUS, LEAF = 0.1, 4, 40, 10.0, 0.2
-    NS = args.scans or 90
-    seed = 3
+CFG3 = dict(ds=0.1, max_iter=4, kd_step=40, radius=10.0, leaf=0.2, seed=3)
+
+
+def cfg3_workload(NS):
+    """BASELINE configs[2]: Livox HAP (120 x 25 deg, non-repetitive: fresh random directions every frame), 240 000 rays per scan."""
+    from better_fastlio2_b200 import synth
+    seed = CFG3["seed"]
     rng = np.random.default_rng(seed)
     dz = -bench.SENSOR_HEIGHT
     world = synth.city_world(half_extent=400.0, seed=seed).shifted((0.0, 0.0, dz))
     truths = [synth.trajectory_state(k, speed=10.0, z=1.8 + dz) for k in range(NS)]
-    t0 = time.perf_counter()
     scans = gen_scans(world, truths, "hap", seed, per_frame_dirs=True)
     priors = [synth.perturb_state(st, rng, 0.05, 0.5) for st in truths]
     # pre-filled map: the forward corridor the narrow field of view sees over the first kd_step frames (afterwards the map
     # is what recontructIKdTree builds from the key frames)
-    mp = synth.sample_surface_map(world, (60.0, 0.0, 0.0), (110.0, 70.0, 1e3), DS3, rng, zmax=25.0 + dz)
+    mp = synth.sample_surface_map(world, (60.0, 0.0, 0.0), (110.0, 70.0, 1e3), CFG3["ds"], rng, zmax=25.0 + dz)
+    return dict(map=mp, scans=scans, priors=priors, truths=truths, P=synth.default_cov())
+
+
+def run_cfg3(args):
+    import torch
+    from better_fastlio2_b200 import capi, synth
+    DS3, MAXIT, KD_STEP, RADIUS, LEAF = CFG3["ds"], CFG3["max_iter"], CFG3["kd_step"], CFG3["radius"], CFG3["leaf"]
+    NS = args.scans or 90
+    t0 = time.perf_counter()
+    work = cfg3_workload(NS)
+    mp, scans, priors, truths = work["map"], work["scans"], work["priors"], work["truths"]
     bench.log(f"cfg3 workload: {NS} scans of ~{np.mean([len(s) for s in scans]):.0f} pts, map {len(mp)} pts, gen {time.perf_counter() - t0:.1f}s")
-    work = dict(map=mp, scans=scans, priors=priors, truths=truths, P=synth.default_cov())
     tree = capi.KDTree(voxel_size=DS3, max_points=32 << 20, max_blocks=4 << 20)
     bench.build_map(tree, mp)
     fov_kw = dict(cube_len=1000.0, det_range=100.0)
@@ -195,23 +205,32 @@ def tri(k, period):
     return p if p <= period else 2 * period - p
 
 
-def run_cfg4(args):
-    import torch
-    from better_fastlio2_b200 import capi, synth
-    DS4, MAXIT = 0.2, 3
-    NS = args.scans or 2000
-    LEG = 360          # frames per leg of the ping-pong (1 m per frame)
-    seed = 4
+CFG4 = dict(ds=0.2, max_iter=3, leg=360, seed=4)
+
+
+def cfg4_workload(NS):
+    """BASELINE configs[3]: Ouster-64 (64 x 1024 rays), ~10M-point map, ping-pong along the street (1 m per frame, legs of 360 m)."""
+    from better_fastlio2_b200 import synth
+    seed, LEG = CFG4["seed"], CFG4["leg"]
     rng = np.random.default_rng(seed)
     dz = -bench.SENSOR_HEIGHT
     world = synth.city_world(half_extent=400.0, seed=seed).shifted((0.0, 0.0, dz))
     truths = [synth.trajectory_state(tri(k, LEG) - LEG // 2, speed=10.0, z=1.8 + dz) for k in range(NS)]
-    t0 = time.perf_counter()
     scans = gen_scans(world, truths, "os64", seed)
     priors = [synth.perturb_state(st, rng, 0.05, 0.5) for st in truths]
-    mp = synth.sample_surface_map(world, (0.0, 0.0, 0.0), (LEG / 2 + 105.0, 196.0, 1e3), DS4, rng, zmax=25.0 + dz)   # ~10M points
+    mp = synth.sample_surface_map(world, (0.0, 0.0, 0.0), (LEG / 2 + 105.0, 196.0, 1e3), CFG4["ds"], rng, zmax=25.0 + dz)   # ~10M points
+    return dict(map=mp, scans=scans, priors=priors, truths=truths, P=synth.default_cov())
+
+
+def run_cfg4(args):
+    import torch
+    from better_fastlio2_b200 import capi, synth
+    DS4, MAXIT = CFG4["ds"], CFG4["max_iter"]
+    NS = args.scans or 2000
+    t0 = time.perf_counter()
+    work = cfg4_workload(NS)
+    mp, scans, priors, truths = work["map"], work["scans"], work["priors"], work["truths"]
     bench.log(f"cfg4 workload: {NS} scans of ~{np.mean([len(s) for s in scans]):.0f} pts, map {len(mp)} pts, gen {time.perf_counter() - t0:.1f}s")
-    work = dict(map=mp, scans=scans, priors=priors, truths=truths, P=synth.default_cov())
     free0, total = torch.cuda.mem_get_info(0)
     tree = capi.KDTree(voxel_size=DS4, max_points=32 << 20, max_blocks=4 << 20)
     bench.build_map(tree, mp)

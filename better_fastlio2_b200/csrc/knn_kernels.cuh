@@ -202,216 +202,6 @@ __device__ __forceinline__ float cover2(float qx, float qy, float qz, float lx, 
   return c > 0.f ? c * c : 0.f;
 }
 
-// Scan the blocks flagged in `todo` (one candidate block per lane: its index `myblk`, occupancy `mymask` and block
-// coordinates) with the WHOLE warp: four blocks per step, lane l reads slots l and l+32 of each, so the 8 point loads of
-// a step are issued back to back (memory-level parallelism) before the insertions.  Voxels inside the phase-A
-// stencil (|v - cv| <= 2) were already visited and are skipped when skip_stencil is set.
-template <int K>
-__device__ __forceinline__ void coop_scan_blocks(const MapDev& m, unsigned todo, int myblk, unsigned long long mymask, int mybx,
-                                                 int myby, int mybz, int lane, float qx, float qy, float qz, int cvx, int cvy,
-                                                 int cvz, bool skip_stencil, float limit, TopK<K>& t) {
-  constexpr int NB = 4;
-  while (todo) {
-    float4 e[2 * NB];
-    bool v[2 * NB];
-#pragma unroll
-    for (int u = 0; u < NB; ++u) {
-      const int src = todo ? __ffs(todo) - 1 : -1;
-      todo &= todo - 1;   // (0 stays 0)
-      const int sl = src >= 0 ? src : 0;
-      const int blk = __shfl_sync(FULL, myblk, sl);
-      const unsigned long long mask = __shfl_sync(FULL, mymask, sl);
-      const int bx = __shfl_sync(FULL, mybx, sl), by = __shfl_sync(FULL, myby, sl), bz = __shfl_sync(FULL, mybz, sl);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int s = lane + 32 * h;
-        bool ok = src >= 0 && ((mask >> s) & 1ull);
-        if (ok && skip_stencil) {
-          const int vx = bx * 4 + (s & 3), vy = by * 4 + ((s >> 2) & 3), vz = bz * 4 + (s >> 4);
-          ok = !(abs(vx - cvx) <= 2 && abs(vy - cvy) <= 2 && abs(vz - cvz) <= 2);
-        }
-        v[u * 2 + h] = ok;
-        if (ok) e[u * 2 + h] = __ldg(&m.slots[(size_t)blk * 64 + s]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 2 * NB; ++j) {
-      if (!v[j]) continue;
-      const float4 p = e[j];
-      const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
-      if (dd <= limit) t.insert(dd, p.x, p.y, p.z);
-      walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
-        const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-        if (d2 <= limit) t.insert(d2, o.x, o.y, o.z);
-      });
-    }
-  }
-}
-
-// Process the blocks of one coarse cell (slot cs): per 32-bit group of the 512-bit block bitmap every lane tests its
-// block (bit set, not already covered by phase B0, box distance within the bound), probes the hash for it in
-// parallel, then the candidates are scanned co-operatively.
-template <int K>
-__device__ __forceinline__ void scan_coarse_cell(const MapDev& m, int cs, int lane, float qx, float qy, float qz,
-                                                 int cvx, int cvy, int cvz, bool have, float thr, float lim, float mg,
-                                                 TopK<K>& t) {
-  const int qbx_ = cvx >> 2, qby_ = cvy >> 2, qbz_ = cvz >> 2;
-  int ccx, ccy, ccz;
-  unpack_key(__ldg(&m.ckeys[cs]), ccx, ccy, ccz);
-  const float ds = m.ds;
-  const float bs = 4.f * ds;
-  const float bound = have ? thr : CUDART_INF_F;
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    const unsigned long long word = __ldg(&m.cbits[(size_t)cs * 8 + k]);
-    if (word == 0ull) continue;  // uniform
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      const int bit = k * 64 + h * 32 + lane;
-      const int bx = ccx * 8 + (bit & 7), by = ccy * 8 + ((bit >> 3) & 7), bz = ccz * 8 + (bit >> 6);
-      bool go = (word >> (h * 32 + lane)) & 1ull;
-      if (go && abs(bx - qbx_) <= BLOCK_RINGS && abs(by - qby_) <= BLOCK_RINGS && abs(bz - qbz_) <= BLOCK_RINGS) go = false;  // visited by phase B0
-      if (go) {
-        const float lx = (float)bx * bs, ly = (float)by * bs, lz = (float)bz * bs;
-        const float md = box_mind2(qx, qy, qz, lx, ly, lz, lx + bs, ly + bs, lz + bs, mg);
-        go = !(md > bound || md > lim);
-      }
-      int blk = -1;
-      unsigned long long mask = 0ull;
-      if (go) blk = find_block_mask(m, pack_key(bx, by, bz), mask);
-      const unsigned todo = __ballot_sync(FULL, blk >= 0 && mask != 0ull);
-      if (todo) coop_scan_blocks<K>(m, todo, blk, mask, bx, by, bz, lane, qx, qy, qz, cvx, cvy, cvz, false, fminf(lim, bound), t);
-    }
-  }
-}
-
-// Finish ONE query with the whole warp over the coarse levels (rare: map frontier).  A real call (noinline) so that its
-// register needs do not inflate the group kernel; wcount/wthr/seed = state of the query after the block rings (lane r
-// passes result r in sd,sx,sy,sz).
-template <int K>
-__device__ __noinline__ void warp_finish_coarse(MapDev m, float4* nbr, unsigned char* cnt, int* phase_stats, int stride, float lim,
-                                                int qi, float wqx, float wqy, float wqz, int wcount, float wthr, float sd, float sx,
-                                                float sy, float sz) {
-  const int lane = threadIdx.x & 31;
-  const float ds = m.ds;
-    TopK<K> tw;
-    tw.clear();
-    float wd_ = CUDART_INF_F, wx = CUDART_NAN_F, wy = CUDART_NAN_F, wz = CUDART_NAN_F;
-    if (lane < wcount) { wd_ = sd; wx = sx; wy = sy; wz = sz; tw.d[0] = sd; tw.x[0] = sx; tw.y[0] = sy; tw.z[0] = sz; }
-    const int cvx = voxel_of(wqx, ds), cvy = voxel_of(wqy, ds), cvz = voxel_of(wqz, ds);
-    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(wqx) + fabsf(wqy) + fabsf(wqz));
-    const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
-    int phase = 2;
-    {
-      // ---------------- phase B: 3x3x3 coarse cells around the query
-      const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
-      int mycs = -1;
-      if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
-      // nearest cells first (centre cell), so the bound tightens early
-      const unsigned present = __ballot_sync(FULL, mycs >= 0);
-      {
-        const int cs = __shfl_sync(FULL, mycs, 13);
-        if (cs >= 0) scan_coarse_cell<K>(m, cs, lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
-        if (wcount < K) wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);  // get a finite bound before the ring
-      }
-      unsigned rest = present & ~(1u << 13);
-      while (rest) {
-        const int c = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const int cs = __shfl_sync(FULL, mycs, c);
-        scan_coarse_cell<K>(m, cs, lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
-      }
-      wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
-      const float cs32 = 32.f * ds;
-      const float cov = cover2(wqx, wqy, wqz, (float)(qcx - 1) * cs32, (float)(qcy - 1) * cs32, (float)(qcz - 1) * cs32,
-                               (float)(qcx + 2) * cs32, (float)(qcy + 2) * cs32, (float)(qcz + 2) * cs32, mg);
-      const bool wdone = (wcount == K && wthr < cov) || cov > lim;
-      if (!wdone) {
-        // ---------------- phase C: every other coarse cell of the map, pruned by its box distance.  Nearest first: while the
-        // query has no k-th distance yet (far outside the map: nothing to prune with), the cell(s) at the smallest box distance
-        // not visited so far are scanned and merged — the first one or two give a bound that prunes almost all of the rest —
-        // then one sweep over the remaining cells with that bound.
-        phase = 3;
-        const int ncs = m.counters[CNT_COARSE_USED];   // dense list of occupied coarse cells
-        auto cell_md = [&](int li, int& cs) -> float {   // box distance of list entry li (INF: no cell / inside the 3x3x3 already done)
-          cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
-          const uint64_t ck = cs >= 0 ? __ldg(&m.ckeys[cs]) : KEY_EMPTY;
-          if (ck == KEY_EMPTY) return CUDART_INF_F;
-          int cx, cy, cz;
-          unpack_key(ck, cx, cy, cz);
-          if (abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1) return CUDART_INF_F;
-          return box_mind2(wqx, wqy, wqz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32, (float)(cx + 1) * cs32,
-                           (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
-        };
-        float level = -1.f;   // cells with md <= level have been scanned
-#pragma unroll 1
-        for (int iter = 0; iter < 16 && wcount < K; ++iter) {
-          float best = CUDART_INF_F;
-#pragma unroll 1
-          for (int base = 0; base < ncs; base += 32) {
-            int cs;
-            const float md = cell_md(base + lane, cs);
-            if (md > level && md <= lim) best = fminf(best, md);
-          }
-          best = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(best)));   // (non-negative floats order like their bits)
-          if (!(best < CUDART_INF_F)) break;
-#pragma unroll 1
-          for (int base = 0; base < ncs; base += 32) {
-            int cs;
-            const float md = cell_md(base + lane, cs);
-            unsigned todo = __ballot_sync(FULL, md == best);
-            while (todo) {
-              const int c = __ffs(todo) - 1;
-              todo &= todo - 1;
-              scan_coarse_cell<K>(m, __shfl_sync(FULL, cs, c), lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
-            }
-          }
-          wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
-          level = best;
-        }
-#pragma unroll 1
-        for (int base = 0; base < ncs; base += 32) {
-          int cs;
-          const float md = cell_md(base + lane, cs);
-          const bool go = md > level && md < CUDART_INF_F && (wcount < K || md <= wthr) && md <= lim;
-          unsigned todo = __ballot_sync(FULL, go);
-          if (!todo) continue;
-          while (todo) {
-            const int c = __ffs(todo) - 1;
-            todo &= todo - 1;
-            scan_coarse_cell<K>(m, __shfl_sync(FULL, cs, c), lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
-          }
-          wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
-        }
-      }
-    }
-    if (lane < K) nbr[(size_t)lane * stride + qi] = make_float4(wx, wy, wz, wd_);
-    if (lane == 0) {
-      cnt[qi] = (unsigned char)wcount;
-      if (phase_stats) atomicAdd(&phase_stats[phase], 1);
-    }
-}
-
-// K1b: exact completion of the queries the stencil kernel could not prove complete (its work list).  The stencil
-// kernel has already visited the whole 5x5x5 voxel stencil and left its (up to K) best points in the neighbour cache:
-// they seed the search, which then only looks OUTSIDE the stencil.  One WARP per query, work claimed by atomic tickets.
-//
-// The kernel is a chain of dependent memory round trips per query, so it is built to keep that chain short:
-//   ring r (shell of blocks at Chebyshev block distance r around the query block, r = 1..EXACT_RINGS):
-//     1. the shell positions are enumerated 128 at a time (4 per lane); each is pruned by its box distance against the
-//        current k-th distance, and from ring 3 on by the block-occupancy bitmaps of the 3x3x3 coarse cells around the query
-//        (staged once into shared memory), so that only blocks that exist and can matter are probed;
-//     2. ONE round trip fetches the 32-byte hash entries (block index + voxel occupancy) of all surviving positions;
-//     3. the occupancy words are cut down by the 5^3 stencil (ring 1) and by a separable per-axis slab test against the
-//        k-th distance; the surviving voxels of ALL blocks of the round are compacted into one candidate list in shared
-//        memory (each lane pushes its blocks' voxels at the offset given by a warp prefix sum);
-//     4. the list is consumed 128 candidates at a time: four independent 16-byte point loads per lane and round trip,
-//        then the insertions into lane-local sorted lists;
-//     5. one K-round warp merge per ring gives the new k-th distance and the completeness test
-//        (d_k < distance to the boundary of the searched cube).
-//   Queries still open after ring EXACT_RINGS (nothing within ~6 m at 0.2 m voxels: far outside the map) are finished over
-//   the coarse levels by warp_finish_coarse (remaining blocks of the 3x3x3 coarse cells, then every coarse cell with
-//   box-distance pruning).
 constexpr int EXACT_RINGS = 8;     // rings searched through the 27 staged coarse bitmaps: (q_block +- 8) stays inside them
 constexpr int CAND_CAP = 512;      // per-warp candidate list capacity (voxel slot ids)
 
@@ -456,6 +246,267 @@ __device__ __forceinline__ unsigned axis_slabs_within(int b, float q, float ds, 
   return m;
 }
 
+// One batch of candidate BLOCKS for one query, processed by the whole warp (the core of the exact kernel): `nb` positions
+// (pos(idx, bx, by, bz) -> false to skip one) are taken 128 at a time; each is pruned by its box distance against `bound`,
+// ONE round trip fetches the 32-byte hash entries (block index + voxel occupancy) of the survivors, the occupancy words are
+// cut down (5^3 stencil already seen when cut_stencil; per-axis slab tests against `bound`), the surviving voxels of ALL
+// blocks of the round are compacted into one candidate list in shared memory (warp prefix sum; every lane pushes its
+// blocks' voxels) and consumed 128 at a time: four independent 16-byte point loads per lane and round trip, then the
+// insertions into the lane-local sorted lists `t`.
+template <int K, class PosFn>
+__device__ __forceinline__ void exact_block_batch(const MapDev& m, unsigned* cand, int lane, int nb, PosFn pos, float qx, float qy,
+                                                  float qz, int cvx, int cvy, int cvz, float mg, float bound, bool cut_stencil,
+                                                  TopK<K>& t) {
+  const float ds = m.ds, bs4 = 4.f * ds;
+#pragma unroll 1
+  for (int base = 0; base < nb; base += 128) {
+    int blk[4];
+    uint4 ent[4];
+    unsigned long long mask[4];
+    int bxs[4], bys[4], bzs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + 32 * u + lane;
+      blk[u] = -2;   // -2: no probe issued
+      mask[u] = 0ull;
+      bxs[u] = bys[u] = bzs[u] = 0;
+      if (idx < nb) {
+        int bx, by, bz;
+        if (pos(idx, bx, by, bz)) {
+          bxs[u] = bx; bys[u] = by; bzs[u] = bz;
+          const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
+          if (!(box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg) > bound)) {
+            const uint32_t hs = hash_key(pack_key(bx, by, bz)) & m.hash_mask;
+            const HEntry* he = &m.hent[hs];
+            ent[u] = __ldg(reinterpret_cast<const uint4*>(he));
+            mask[u] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));   // same 32-B sector
+            prefetch_next_entry(m, hs);
+            blk[u] = -1;
+          }
+        }
+      }
+    }
+    int c = 0;   // this lane's candidate voxels of the round
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (blk[u] == -1) {
+        const uint64_t key = pack_key(bxs[u], bys[u], bzs[u]);
+        const uint64_t k0 = ((uint64_t)ent[u].y << 32) | ent[u].x;
+        if (k0 == key) blk[u] = (int)ent[u].z;
+        else if (k0 == KEY_EMPTY) { blk[u] = -1; mask[u] = 0ull; }
+        else blk[u] = find_block_mask(m, key, mask[u]);   // collision: sequential probe
+        if (blk[u] >= 0 && mask[u]) {
+          if (cut_stencil) mask[u] &= ~block_stencil_mask(bxs[u], bys[u], bzs[u], cvx, cvy, cvz);
+          if (bound < CUDART_INF_F)
+            mask[u] &= mask_from_axes(axis_slabs_within(bxs[u], qx, ds, mg, bound), axis_slabs_within(bys[u], qy, ds, mg, bound),
+                                      axis_slabs_within(bzs[u], qz, ds, mg, bound));
+        } else mask[u] = 0ull;
+      } else mask[u] = 0ull;
+      c += __popcll(mask[u]);
+    }
+    // ---- compaction: exclusive prefix of the per-lane candidate counts
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int T = __shfl_sync(FULL, incl, 31);
+    if (T == 0) continue;   // warp-uniform
+    const int mybase = incl - c;
+#pragma unroll 1
+    for (int chunk = 0; chunk < T; chunk += CAND_CAP) {
+      int p0 = mybase - chunk;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        unsigned long long mm = mask[u];
+        const unsigned pb = (unsigned)blk[u] * 64u;
+        while (mm) {
+          const int sl = __ffsll((long long)mm) - 1;
+          mm &= mm - 1;
+          if ((unsigned)p0 < (unsigned)CAND_CAP) cand[p0] = pb + (unsigned)sl;
+          ++p0;
+        }
+      }
+      __syncwarp();
+      const int n = min(T - chunk, CAND_CAP);
+#pragma unroll 1
+      for (int j0 = 0; j0 < n; j0 += 128) {
+        float4 e[4];
+        bool ok[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int j = j0 + 32 * v + lane;
+          ok[v] = j < n;
+          if (ok[v]) e[v] = __ldg(&m.slots[cand[j]]);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (ok[v]) {
+            const float4 p = e[v];
+            const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
+            if (dd <= bound) t.insert(dd, p.x, p.y, p.z);
+            walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
+              const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+              if (d2 <= bound) t.insert(d2, o.x, o.y, o.z);
+            });
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// All blocks of one coarse cell (slot cs) that can still matter: its 512-bit block bitmap is staged in the warp's shared
+// memory (`cb`, 8 words) and the cell's blocks go through exact_block_batch; blocks within BLOCK_RINGS of the query block
+// were visited by the rings and are skipped.
+template <int K>
+__device__ __forceinline__ void scan_coarse_cell(const MapDev& m, unsigned* cand, unsigned long long* cb, int cs, int lane, float qx,
+                                                 float qy, float qz, int cvx, int cvy, int cvz, bool have, float thr, float lim,
+                                                 float mg, TopK<K>& t) {
+  const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+  int ccx, ccy, ccz;
+  unpack_key(__ldg(&m.ckeys[cs]), ccx, ccy, ccz);
+  __syncwarp();
+  if (lane < 8) cb[lane] = __ldg(&m.cbits[(size_t)cs * 8 + lane]);
+  __syncwarp();
+  const float bound = fminf(have ? thr : CUDART_INF_F, lim);
+  exact_block_batch<K>(m, cand, lane, 512, [&](int idx, int& bx, int& by, int& bz) -> bool {
+    if (!((cb[idx >> 6] >> (idx & 63)) & 1ull)) return false;
+    bx = ccx * 8 + (idx & 7); by = ccy * 8 + ((idx >> 3) & 7); bz = ccz * 8 + (idx >> 6);
+    return !(abs(bx - qbx) <= BLOCK_RINGS && abs(by - qby) <= BLOCK_RINGS && abs(bz - qbz) <= BLOCK_RINGS);
+  }, qx, qy, qz, cvx, cvy, cvz, mg, bound, false, t);
+}
+
+// Finish ONE query with the whole warp over the coarse levels (rare: map frontier).  A real call (noinline) so that its
+// register needs do not inflate the group kernel; wcount/wthr/seed = state of the query after the block rings (lane r
+// passes result r in sd,sx,sy,sz).
+template <int K>
+__device__ __noinline__ void warp_finish_coarse(MapDev m, unsigned* cand, unsigned long long* cb, float4* nbr, unsigned char* cnt,
+                                                int* phase_stats, int stride, float lim,
+                                                int qi, float wqx, float wqy, float wqz, int wcount, float wthr, float sd, float sx,
+                                                float sy, float sz) {
+  const int lane = threadIdx.x & 31;
+  const float ds = m.ds;
+    TopK<K> tw;
+    tw.clear();
+    float wd_ = CUDART_INF_F, wx = CUDART_NAN_F, wy = CUDART_NAN_F, wz = CUDART_NAN_F;
+    if (lane < wcount) { wd_ = sd; wx = sx; wy = sy; wz = sz; tw.d[0] = sd; tw.x[0] = sx; tw.y[0] = sy; tw.z[0] = sz; }
+    const int cvx = voxel_of(wqx, ds), cvy = voxel_of(wqy, ds), cvz = voxel_of(wqz, ds);
+    const float mg = 1e-3f * ds + 4.8e-7f * (fabsf(wqx) + fabsf(wqy) + fabsf(wqz));
+    const int qbx = cvx >> 2, qby = cvy >> 2, qbz = cvz >> 2;
+    int phase = 2;
+    {
+      // ---------------- phase B: 3x3x3 coarse cells around the query
+      const int qcx = qbx >> 3, qcy = qby >> 3, qcz = qbz >> 3;
+      int mycs = -1;
+      if (lane < 27) mycs = find_coarse(m, pack_key(qcx + (lane % 3) - 1, qcy + ((lane / 3) % 3) - 1, qcz + (lane / 9) - 1));
+      // nearest cells first (centre cell), so the bound tightens early
+      const unsigned present = __ballot_sync(FULL, mycs >= 0);
+      {
+        const int cs = __shfl_sync(FULL, mycs, 13);
+        if (cs >= 0) scan_coarse_cell<K>(m, cand, cb, cs, lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+        if (wcount < K) wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);  // get a finite bound before the ring
+      }
+      unsigned rest = present & ~(1u << 13);
+      while (rest) {
+        const int c = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int cs = __shfl_sync(FULL, mycs, c);
+        scan_coarse_cell<K>(m, cand, cb, cs, lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+      }
+      wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
+      const float cs32 = 32.f * ds;
+      const float cov = cover2(wqx, wqy, wqz, (float)(qcx - 1) * cs32, (float)(qcy - 1) * cs32, (float)(qcz - 1) * cs32,
+                               (float)(qcx + 2) * cs32, (float)(qcy + 2) * cs32, (float)(qcz + 2) * cs32, mg);
+      const bool wdone = (wcount == K && wthr < cov) || cov > lim;
+      if (!wdone) {
+        // ---------------- phase C: every other coarse cell of the map, pruned by its box distance.  Nearest first: while the
+        // query has no k-th distance yet (far outside the map: nothing to prune with), the cell(s) at the smallest box distance
+        // not visited so far are scanned and merged — the first one or two give a bound that prunes almost all of the rest —
+        // then one sweep over the remaining cells with that bound.
+        phase = 3;
+        const int ncs = m.counters[CNT_COARSE_USED];   // dense list of occupied coarse cells
+        auto cell_md = [&](int li, int& cs) -> float {   // box distance of list entry li (INF: no cell / inside the 3x3x3 already done)
+          cs = li < ncs ? (int)__ldg(&m.clist[li]) : -1;
+          const uint64_t ck = cs >= 0 ? __ldg(&m.ckeys[cs]) : KEY_EMPTY;
+          if (ck == KEY_EMPTY) return CUDART_INF_F;
+          int cx, cy, cz;
+          unpack_key(ck, cx, cy, cz);
+          if (abs(cx - qcx) <= 1 && abs(cy - qcy) <= 1 && abs(cz - qcz) <= 1) return CUDART_INF_F;
+          return box_mind2(wqx, wqy, wqz, (float)cx * cs32, (float)cy * cs32, (float)cz * cs32, (float)(cx + 1) * cs32,
+                           (float)(cy + 1) * cs32, (float)(cz + 1) * cs32, mg);
+        };
+        float level = -1.f;   // cells with md <= level have been scanned
+#pragma unroll 1
+        for (int iter = 0; iter < 16 && wcount < K; ++iter) {
+          float best = CUDART_INF_F;
+#pragma unroll 1
+          for (int base = 0; base < ncs; base += 32) {
+            int cs;
+            const float md = cell_md(base + lane, cs);
+            if (md > level && md <= lim) best = fminf(best, md);
+          }
+          best = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(best)));   // (non-negative floats order like their bits)
+          if (!(best < CUDART_INF_F)) break;
+#pragma unroll 1
+          for (int base = 0; base < ncs; base += 32) {
+            int cs;
+            const float md = cell_md(base + lane, cs);
+            unsigned todo = __ballot_sync(FULL, md == best);
+            while (todo) {
+              const int c = __ffs(todo) - 1;
+              todo &= todo - 1;
+              scan_coarse_cell<K>(m, cand, cb, __shfl_sync(FULL, cs, c), lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+            }
+          }
+          wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
+          level = best;
+        }
+#pragma unroll 1
+        for (int base = 0; base < ncs; base += 32) {
+          int cs;
+          const float md = cell_md(base + lane, cs);
+          const bool go = md > level && md < CUDART_INF_F && (wcount < K || md <= wthr) && md <= lim;
+          unsigned todo = __ballot_sync(FULL, go);
+          if (!todo) continue;
+          while (todo) {
+            const int c = __ffs(todo) - 1;
+            todo &= todo - 1;
+            scan_coarse_cell<K>(m, cand, cb, __shfl_sync(FULL, cs, c), lane, wqx, wqy, wqz, cvx, cvy, cvz, wcount == K, wthr, lim, mg, tw);
+          }
+          wcount = warp_merge<K>(tw, FULL, lane, lane, wd_, wx, wy, wz, wthr);
+        }
+      }
+    }
+    if (lane < K) nbr[(size_t)lane * stride + qi] = make_float4(wx, wy, wz, wd_);
+    if (lane == 0) {
+      cnt[qi] = (unsigned char)wcount;
+      if (phase_stats) atomicAdd(&phase_stats[phase], 1);
+    }
+}
+
+// K1b: exact completion of the queries the stencil kernel could not prove complete (its work list).  The stencil
+// kernel has already visited the whole 5x5x5 voxel stencil and left its (up to K) best points in the neighbour cache:
+// they seed the search, which then only looks OUTSIDE the stencil.  One WARP per query, work claimed by atomic tickets.
+//
+// The kernel is a chain of dependent memory round trips per query, so it is built to keep that chain short:
+//   ring r (shell of blocks at Chebyshev block distance r around the query block, r = 1..EXACT_RINGS):
+//     1. the shell positions are enumerated 128 at a time (4 per lane); each is pruned by its box distance against the
+//        current k-th distance, and from ring 3 on by the block-occupancy bitmaps of the 3x3x3 coarse cells around the query
+//        (staged once into shared memory), so that only blocks that exist and can matter are probed;
+//     2. ONE round trip fetches the 32-byte hash entries (block index + voxel occupancy) of all surviving positions;
+//     3. the occupancy words are cut down by the 5^3 stencil (ring 1) and by a separable per-axis slab test against the
+//        k-th distance; the surviving voxels of ALL blocks of the round are compacted into one candidate list in shared
+//        memory (each lane pushes its blocks' voxels at the offset given by a warp prefix sum);
+//     4. the list is consumed 128 candidates at a time: four independent 16-byte point loads per lane and round trip,
+//        then the insertions into lane-local sorted lists;
+//     5. one K-round warp merge per ring gives the new k-th distance and the completeness test
+//        (d_k < distance to the boundary of the searched cube).
+//   Queries still open after ring EXACT_RINGS (nothing within ~6 m at 0.2 m voxels: far outside the map) are finished over
+//   the coarse levels by warp_finish_coarse (remaining blocks of the 3x3x3 coarse cells, then every coarse cell with
+//   box-distance pruning).
 template <int K>
 __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
   pdl_sync();
@@ -529,113 +580,18 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       const float bound = fminf(gcount == K ? thr : CUDART_INF_F, lim);
       const int wd = 2 * r + 1;
       const int nb = (r == 1) ? 27 : wd * wd * wd - (wd - 2) * (wd - 2) * (wd - 2);
-#pragma unroll 1
-      for (int base = 0; base < nb; base += 128) {
-        int blk[4];
-        uint4 ent[4];
-        unsigned long long mask[4];
-        int bxs[4], bys[4], bzs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + 32 * u + lane;
-          blk[u] = -2;   // -2: no probe issued
-          mask[u] = 0ull;
-          if (idx < nb) {
-            int dx, dy, dz;
-            if (r == 1) { dx = idx % 3 - 1; dy = (idx / 3) % 3 - 1; dz = idx / 9 - 1; }   // incl. the query's own block: its
-            else shell_offset(r, idx, dx, dy, dz);                                         // voxels outside the stencil are unseen
-            const int bx = qbx + dx, by = qby + dy, bz = qbz + dz;
-            bxs[u] = bx; bys[u] = by; bzs[u] = bz;
-            const float lx = (float)bx * bs4, ly = (float)by * bs4, lz = (float)bz * bs4;
-            bool go = !(box_mind2(qx, qy, qz, lx, ly, lz, lx + bs4, ly + bs4, lz + bs4, mg) > bound);
-            if (go && r >= 3) {
-              const int cell = ((bz >> 3) - (qcz - 1)) * 9 + ((by >> 3) - (qcy - 1)) * 3 + ((bx >> 3) - (qcx - 1));
-              const int bit = ((bz & 7) << 6) | ((by & 7) << 3) | (bx & 7);
-              go = (cb[cell * 8 + (bit >> 6)] >> (bit & 63)) & 1ull;
-            }
-            if (go) {
-              const uint32_t hs = hash_key(pack_key(bx, by, bz)) & m.hash_mask;
-              const HEntry* he = &m.hent[hs];
-              ent[u] = __ldg(reinterpret_cast<const uint4*>(he));
-              mask[u] = __ldg(reinterpret_cast<const unsigned long long*>(&he->mask));   // same 32-B sector
-              prefetch_next_entry(m, hs);
-              blk[u] = -1;
-            }
-          }
+      exact_block_batch<K>(m, cand, lane, nb, [&](int idx, int& bx, int& by, int& bz) -> bool {
+        int dx, dy, dz;
+        if (r == 1) { dx = idx % 3 - 1; dy = (idx / 3) % 3 - 1; dz = idx / 9 - 1; }   // incl. the query's own block: its
+        else shell_offset(r, idx, dx, dy, dz);                                         // voxels outside the stencil are unseen
+        bx = qbx + dx; by = qby + dy; bz = qbz + dz;
+        if (r >= 3) {   // (rings 3..8 lie inside the staged 3x3x3 coarse cells: only blocks that exist are probed)
+          const int cell = ((bz >> 3) - (qcz - 1)) * 9 + ((by >> 3) - (qcy - 1)) * 3 + ((bx >> 3) - (qcx - 1));
+          const int bit = ((bz & 7) << 6) | ((by & 7) << 3) | (bx & 7);
+          return (cb[cell * 8 + (bit >> 6)] >> (bit & 63)) & 1ull;
         }
-        int c = 0;   // this lane's candidate voxels of the round
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (blk[u] == -1) {
-            const uint64_t key = pack_key(bxs[u], bys[u], bzs[u]);
-            const uint64_t k0 = ((uint64_t)ent[u].y << 32) | ent[u].x;
-            if (k0 == key) blk[u] = (int)ent[u].z;
-            else if (k0 == KEY_EMPTY) { blk[u] = -1; mask[u] = 0ull; }
-            else blk[u] = find_block_mask(m, key, mask[u]);   // collision: sequential probe
-            if (blk[u] >= 0 && mask[u]) {
-              if (r == 1) mask[u] &= ~block_stencil_mask(bxs[u], bys[u], bzs[u], cvx, cvy, cvz);
-              if (bound < CUDART_INF_F)
-                mask[u] &= mask_from_axes(axis_slabs_within(bxs[u], qx, ds, mg, bound), axis_slabs_within(bys[u], qy, ds, mg, bound),
-                                          axis_slabs_within(bzs[u], qz, ds, mg, bound));
-            } else mask[u] = 0ull;
-          } else mask[u] = 0ull;
-          c += __popcll(mask[u]);
-        }
-        KPH(ph_probe);
-        // ---- compaction: exclusive prefix of the per-lane candidate counts
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(FULL, incl, o);
-          if (lane >= o) incl += v;
-        }
-        const int T = __shfl_sync(FULL, incl, 31);
-        if (T == 0) continue;   // warp-uniform
-        const int mybase = incl - c;
-#pragma unroll 1
-        for (int chunk = 0; chunk < T; chunk += CAND_CAP) {
-          int pos = mybase - chunk;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            unsigned long long mm = mask[u];
-            const unsigned pb = (unsigned)blk[u] * 64u;
-            while (mm) {
-              const int sl = __ffsll((long long)mm) - 1;
-              mm &= mm - 1;
-              if ((unsigned)pos < (unsigned)CAND_CAP) cand[pos] = pb + (unsigned)sl;
-              ++pos;
-            }
-          }
-          __syncwarp();
-          KPH(ph_push);
-          const int n = min(T - chunk, CAND_CAP);
-#pragma unroll 1
-          for (int j0 = 0; j0 < n; j0 += 128) {
-            float4 e[4];
-            bool ok[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const int j = j0 + 32 * v + lane;
-              ok[v] = j < n;
-              if (ok[v]) e[v] = __ldg(&m.slots[cand[j]]);
-            }
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              if (ok[v]) {
-                const float4 p = e[v];
-                const float dd = sqdist(qx, qy, qz, p.x, p.y, p.z);
-                if (dd <= bound) t.insert(dd, p.x, p.y, p.z);
-                walk_chain(m, __float_as_int(p.w), [&](const float4 o, int) {
-                  const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-                  if (d2 <= bound) t.insert(d2, o.x, o.y, o.z);
-                });
-              }
-            }
-          }
-          __syncwarp();
-          KPH(ph_load);
-        }
-      }
+        return true;
+      }, qx, qy, qz, cvx, cvy, cvz, mg, bound, r == 1, t);
       KPH(ph_probe);
       // ---- merge the lane-local lists: new k-th distance, completeness of the searched cube
       gcount = warp_merge<K>(t, FULL, lane, lane, rd, rx, ry, rz, thr);
@@ -664,7 +620,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
     // are skipped inside scan_coarse_cell)
     if (!done) {
       __syncwarp();
-      warp_finish_coarse<K>(m, a.nbr, a.cnt, a.phase_stats, a.stride, lim, i, qx, qy, qz, gcount, thr, rd, rx, ry, rz);
+      warp_finish_coarse<K>(m, cand, cb, a.nbr, a.cnt, a.phase_stats, a.stride, lim, i, qx, qy, qz, gcount, thr, rd, rx, ry, rz);
     }
     if (lane == 0) w = nwarps + atomicAdd(a.work_ticket, 1);
     w = __shfl_sync(FULL, w, 0);

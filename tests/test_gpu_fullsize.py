@@ -120,3 +120,48 @@ def test_full_size_closed_loop_vs_oracle(oracle):
     print("full size, closed loop: median |dpos| = %.3e, max = %.3e m (frame %d), max drot = %.3e rad"
           % (np.median(dpos), dpos.max(), int(dpos.argmax()), drot.max()))
     assert (dpos <= 1e-4).mean() >= 0.8 and dpos.max() <= 2e-3 and drot.max() <= 2e-3, (dpos, drot)
+
+
+def test_cfg3_full_scan_size_vs_oracle(oracle):
+    """BASELINE configs[2] at full scan size: 223k-point Livox HAP scans, 0.1 m voxels, extrinsic estimation on, max_iteration 4
+    (config/hap_livox.yaml:45,54-58) — per-frame posterior vs the CPU oracle, then the recontructIKdTree data path
+    (laserMapping.cpp:612-669) on key frames of that size against the oracle's transform + PCL VoxelGrid restatement."""
+    import bench_configs as bc
+    work = bc.cfg3_workload(3)
+    assert min(len(s) for s in work["scans"]) > 200000
+    tree = capi.KDTree(voxel_size=bc.CFG3["ds"], max_points=32 << 20, max_blocks=4 << 20)
+    bench.build_map(tree, work["map"])
+    par = bc.parity_frames(capi, oracle, synth, work, bc.CFG3["ds"], bc.CFG3["max_iter"], True, 3, tree,
+                           dict(cube_len=1000.0, det_range=100.0))
+    print("cfg3:", {k: v for k, v in par.items() if k != "what"})
+    assert par["max_dpos_m"] <= 1e-4 and par["max_drot_rad"] <= 1e-4 and par["map_size_diff"] <= 64
+    # sub-map rebuild from three full-size key frames
+    rng = np.random.default_rng(5)
+    clouds = [np.column_stack([s, rng.uniform(0, 255, len(s))]).astype(np.float32) for s in work["scans"]]
+    poses = []
+    for st in work["truths"]:
+        R = synth.quat_to_mat(st[3:7])
+        poses.append([st[0], st[1], st[2], np.arctan2(R[2, 1], R[2, 2]), -np.arcsin(R[2, 0]), np.arctan2(R[1, 0], R[0, 0])])
+    poses = np.array(poses, np.float32)
+    feats = capi.reconstruct_keyframes(tree, [capi.pack_pointtype(c[:, :3], c[:, 3]) for c in clouds], poses, bc.CFG3["leaf"])
+    sub = np.concatenate([oracle.transform_cloud_rpy(c, p) for c, p in zip(clouds, poses)])
+    o, _, _ = oracle.voxel_grid(sub, bc.CFG3["leaf"], order="stable")
+    assert np.array_equal(feats, o) and tree.validnum() == len(o)
+    tree.close()
+
+
+def test_cfg4_full_map_size_vs_oracle(oracle):
+    """BASELINE configs[3]: Ouster-64 scans against a ~10M-point map (config/mulran.yaml:53-57) — per-frame posterior vs the CPU
+    oracle on the first frames, map sizes, and the device memory the library holds for such a map."""
+    import bench_configs as bc
+    work = bc.cfg4_workload(3)
+    assert len(work["map"]) > 10000000
+    tree = capi.KDTree(voxel_size=bc.CFG4["ds"], max_points=32 << 20, max_blocks=4 << 20)
+    bench.build_map(tree, work["map"])
+    assert tree.validnum() > 9500000
+    par = bc.parity_frames(capi, oracle, synth, work, bc.CFG4["ds"], bc.CFG4["max_iter"], False, 3, tree,
+                           dict(cube_len=1000.0, det_range=100.0))
+    print("cfg4:", {k: v for k, v in par.items() if k != "what"})
+    assert par["max_dpos_m"] <= 1e-4 and par["max_drot_rad"] <= 1e-4 and par["map_size_diff"] <= 128
+    assert tree.stats()["device_bytes"] < 8e9
+    tree.close()
