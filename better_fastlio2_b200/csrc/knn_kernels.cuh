@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
     int dbg_rings = 0;
     (void)dbg_rings;
 #ifdef FLB_TRACE
-    long long ph_probe = 0, ph_push = 0, ph_load = 0, ph_merge = 0, ph_mark = clock64();
+    long long ph_probe = 0, ph_merge = 0, ph_mark = clock64();   // (ph_probe: the block batches = probes + compaction + point loads)
     const long long ph_seed = ph_mark - e0;
 #define KPH(acc) { const long long now_ = clock64(); acc += now_ - ph_mark; ph_mark = now_; }
 #else
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       const long long e1 = clock64();
       FLB_DBG_ADD(16, 1); FLB_DBG_ADD(17, e1 - e0); FLB_DBG_MAX(18, e1 - e0); FLB_DBG_ADD(18 + min(dbg_rings, 6), 1);
       FLB_DBG_ADD(25, done ? 0 : 1);
-      FLB_DBG_ADD(32, ph_seed); FLB_DBG_ADD(33, ph_probe); FLB_DBG_ADD(34, ph_push); FLB_DBG_ADD(35, ph_load); FLB_DBG_ADD(36, ph_merge);
+      FLB_DBG_ADD(32, ph_seed); FLB_DBG_ADD(33, ph_probe); FLB_DBG_ADD(36, ph_merge);
     }
 #endif
     // ---------------- still unresolved after the block rings: finish over the coarse levels (the blocks of the rings

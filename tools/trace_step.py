@@ -117,8 +117,8 @@ def main():
               "")
         if dbg_sum[32] > 0:
             print("# exact kernel, cycles/query by phase: " + ", ".join(
-                f"{nm}={dbg_sum[i] / nq:.0f}" for nm, i in (("ticket+seed loads", 32), ("enumerate+probe", 33), ("compaction push", 34),
-                                                            ("point loads+insert", 35), ("merge", 36))))
+                f"{nm}={dbg_sum[i] / nq:.0f}" for nm, i in (("ticket", 32), ("seed loads + block batches (probes, compaction, point loads)", 33),
+                                                            ("merges", 36))))
     if args.pairs > 0:
         # two steps in flight: device time from the first kernel of step k to the last kernel of step k+1, against twice the
         # single-step span -> what the device loses BETWEEN two graph launches (copies, graph start-up)
