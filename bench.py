@@ -673,8 +673,9 @@ def frontier_rows(work, torch, local, S=40):
     post = work["truths"][0].copy()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     errs, lat, launches = [], [], 0
-    e0.record(stream)
     for k in range(1, S + 1):
+        if k == 2:
+            e0.record(stream)     # (scan 1 is the warm-up: it pays the session's graph capture)
         pri = post.copy()
         pri[0:3] += work["truths"][k][0:3] - work["truths"][k - 1][0:3]
         pri[3:7] = work["truths"][k][3:7]
@@ -693,9 +694,12 @@ def frontier_rows(work, torch, local, S=40):
     st = tree.stats()
     ses.close()
     tree.close()
+    S = S - 1
+    lat = lat[1:]
     return {"what": "exploration regime: map = first scan + what map_incremental inserted, chained filter, prior off by ~20 cm / 2 deg; "
-                    "device-resident scans, CUDA events over all steps",
-            "steps": S, "scans_per_s": S / (ms * 1e-3), "ms_per_step": ms / S, "step_ms_max": float(max(lat) * 1e3),
+                    "device-resident scans, CUDA events over all steps after one warm-up scan",
+            "steps": S, "scans_per_s": S / (ms * 1e-3), "ms_per_step": ms / S, "step_ms_p50": float(np.median(lat) * 1e3),
+            "step_ms_max": float(max(lat) * 1e3),
             "pose_err_vs_truth_max_m": max(errs), "pose_err_vs_truth_last_m": errs[-1], "map_valid_end": int(st["valid_points"]),
             "gpu_launches": launches}
 
