@@ -329,6 +329,7 @@ __device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double*
 __global__ void k_esikf_begin(EsikfCtl* c, const double* __restrict__ stage, int* work_counts) {
   pdl_sync();
   FLB_TRACE_BEGIN(0);
+  if (threadIdx.x == 0) c->t_begin = global_timer_ns();
   // the record is 558 doubles: every thread issues its (at most two) 16-byte reads at once — reads of host memory are slow
   // per request, so few wide requests all in flight
   __shared__ double sst[26 + NDOF * NDOF + 4];
@@ -365,15 +366,19 @@ struct StepResult {
   int passes, searches, lastM, t, need_host, pad_;
   int counters[32];
   int cnt2[2];
+  unsigned long long span_ns;   // device time from the start of k_esikf_begin to this kernel (%globaltimer): the step's own
+                                // GPU time without an event pair on the stream between two steps in flight
 };
-__global__ void k_publish(const EsikfCtl* c, const int* __restrict__ counters, const int* __restrict__ cnt2, StepResult* out) {
+__global__ void k_publish(const EsikfCtl* c, const int* __restrict__ counters, const int* __restrict__ cnt2, StepResult* out, int with_tail) {
   pdl_sync();
   const int tid = threadIdx.x;
   for (int i = tid; i < NDOF * NDOF; i += blockDim.x) out->P[i] = c->P[i];
   if (tid < 26) out->x[tid] = c->x[tid];
-  if (tid >= 32 && tid < 64) out->counters[tid - 32] = counters[tid - 32];
   if (tid == 64) { out->last_res = c->last_res; out->passes = c->passes; out->searches = c->searches; out->lastM = c->lastM; out->t = c->t; out->need_host = c->need_host; }
+  if (!with_tail) return;   // counters, counts and span: written by the last insert kernel (StepTail, map_kernels.cuh)
+  if (tid >= 32 && tid < 64) out->counters[tid - 32] = counters[tid - 32];
   if (tid == 65) { out->cnt2[0] = cnt2 ? cnt2[0] : 0; out->cnt2[1] = cnt2 ? cnt2[1] : 0; }
+  if (tid == 66) out->span_ns = global_timer_ns() - c->t_begin;
 }
 
 // One loop iteration of update_iterated_dyn_share_modified is split in two kernels so that the half that only needs
@@ -408,12 +413,15 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
   const int tid = threadIdx.x;
   FLB_TRACE_BEGIN(1 * 8 + c->it + 1);
   const int trace_slot = 1 * 8 + c->it + 1;
-  (void)trace_slot;
+  const int trace_ph = c->it + 1 == 1 ? 72 : 1 << 20;   // phases of the pass-1 launch (normally a pass without a search: this kernel is its critical path)
+  (void)trace_slot; (void)trace_ph;
+  FLB_TRACE_PHASE(trace_ph + 0);
   if (c->finished || c->it >= c->max_iter || c->n <= 0) return;   // uniform
   if (tid >= 32 && tid < 58) { xs[tid - 32] = c->x[tid - 32]; xps[tid - 32] = c->xp[tid - 32]; }
   for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) P[e] = c->Pp[e];
   const double R = c->R;
   __syncthreads();
+  FLB_TRACE_PHASE(trace_ph + 1);   // state / covariance staged
   // x_ [-] x_propagated (:1655) and the projection Jacobians, one sub-manifold per warp
   if (tid == 0) {
     so3_boxminus(xs + 3, xps + 3, dx + 3);
@@ -433,6 +441,7 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
     }
   }
   __syncthreads();
+  FLB_TRACE_PHASE(trace_ph + 2);   // boxminus + Jacobians
   if (tid < 4) { const int i = tid >> 1, j = tid & 1; double s = 0; for (int k = 0; k < 3; ++k) s += Nx[3 * i + k] * Mx[2 * k + j]; J2[tid] = s; }
   __syncthreads();
   if (tid < NDOF) {                                     // dx_new with the SO3 / S2 blocks projected (:1671, :1696)
@@ -448,10 +457,13 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
   b_mul_cols_T<3>(P, 6, J3b, tid);
   b_mul_rows<2>(P, P, 21, J2, tid);                     // S2 block :1683-1703
   b_mul_cols_T<2>(P, 21, J2, tid);
+  FLB_TRACE_PHASE(trace_ph + 3);   // covariance projected
   for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) sc->P[e] = P[e];
   if (tid < MD * MD) L[tid] = P[(tid / MD) * NDOF + (tid % MD)] / R;   // Pr11 (MD x MD)
   __syncthreads();
+  FLB_TRACE_PHASE(trace_ph + 4);   // projected covariance stored
   const double* T11 = b_inverse_spd<MD>(L, T, tid);                    // Pr11^-1
+  FLB_TRACE_PHASE(trace_ph + 5);   // inverse
   if (tid < MD * MD) sc->T11[tid] = T11[tid];
   for (int e = tid; e < NDOF * MD; e += ESIKF_THREADS) {               // Q = Pr[:, 0:MD] T11
     const int i = e / MD, j = e - i * MD;
@@ -459,6 +471,7 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
     for (int k = 0; k < MD; ++k) q += (P[i * NDOF + k] / R) * T11[k * MD + j];
     sc->Q[e] = q;
   }
+  FLB_TRACE_PHASE(trace_ph + 6);   // Q written
   FLB_TRACE_END(trace_slot);
 }
 
@@ -489,23 +502,53 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, 
 #pragma unroll
   for (int u = 0; u < 2; ++u) { const int e = tid + u * ESIKF_THREADS; pQ[u] = e < NDOF * MD ? sc->Q[e] : 0.0; }
   const double pT = tid < MD * MD ? sc->T11[tid] : 0.0;
-  // ---- fixed-order reduction of the per-block partials (role of K2): 2 threads per entry (halves of the block range,
-  // coalesced across the entries), 37 independent loads in flight per thread
-  {
+  // ---- fixed-order reduction of the per-block partials (role of K2)
+  if constexpr (MD == 6) {
+    // without extrinsic estimation the measured subspace has 6 columns: only 21 entries of H^T H, 6 of H^T h, the residual
+    // sum and the row count are ever read below — 29 of the 93 accumulators.  One warp per eighth of the block range, one
+    // lane per entry, every load of a lane in flight at once (a third of the bytes and half the dependent batches of the
+    // general form below).
+    static_assert(ESIKF_THREADS == 256, "eight warps, one per eighth of the partial rows");
+    const int k = tid & 31, w = tid >> 5;
+    int e = -1;
+    if (k < 21) { int i = 0, r = k; while (r >= 6 - i) { r -= 6 - i; ++i; } e = i * 13 - i * (i - 1) / 2 + r; }   // (i, i + r), both < 6
+    else if (k < 27) { const int l = k - 21; e = l * 13 - l * (l - 1) / 2 + (12 - l); }                               // (l, 12)
+    else if (k < 29) e = 91 + (k - 27);                                                                             // residual sum, count
+    double* part = L;   // [8][32]; L is not used before the second __syncthreads below
+    double s = 0.0;
+    if (e >= 0) {
+      const int per = (nblocks + 7) >> 3;
+      const int b0 = min(w * per, nblocks), b1 = min(b0 + per, nblocks);
+      for (int b = b0; b < b1; b += 19) {
+        double v[19];
+#pragma unroll
+        for (int u = 0; u < 19; ++u) v[u] = b + u < b1 ? partial[(size_t)(b + u) * NACC + e] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 19; ++u) s += v[u];
+      }
+    }
+    part[w * 32 + k] = s;
+    __syncthreads();
+    if (w == 0 && e >= 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += part[u * 32 + k];
+      acc[e] = t;
+    }
+  } else {
+    // 2 threads per entry (halves of the block range, coalesced across the entries), 37 independent loads in flight per thread
     const int e = tid & 127, h = tid >> 7;
     double s = 0.0;
     if (e < NACC) {
       const int half = (nblocks + 1) >> 1;
       const int b0 = h ? half : 0, b1 = h ? nblocks : half;
-      int b = b0;
-      for (; b + 37 <= b1; b += 37) {
+      for (int b = b0; b < b1; b += 37) {
         double v[37];
 #pragma unroll
-        for (int u = 0; u < 37; ++u) v[u] = partial[(size_t)(b + u) * NACC + e];
+        for (int u = 0; u < 37; ++u) v[u] = b + u < b1 ? partial[(size_t)(b + u) * NACC + e] : 0.0;
 #pragma unroll
         for (int u = 0; u < 37; ++u) s += v[u];
       }
-      for (; b < b1; ++b) s += partial[(size_t)b * NACC + e];
       if (h) acc2[e] = s;
     }
     __syncthreads();

@@ -347,7 +347,7 @@ static int maybe_rehash(flb_map* m);
 // Insert device points. mode 0: verbatim (Build / Add_Points(false)); 1: downsample (Add_Points(true));
 // 2: classified (map_incremental: cls 1 -> downsample, cls 2 -> verbatim). Asynchronous on m->stream.
 static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls, int n, int mode, const int* skip = nullptr,
-                         const int* n_dev = nullptr, bool prefused = false) {
+                         const int* n_dev = nullptr, bool prefused = false, StepTail tail = StepTail{}) {
   // n_dev != nullptr: n is an upper bound (capacity) used for launch geometry, the real count is read on the device
   if (n <= 0) return 0;
   const int g = grid_for(n, 256, m->sm_count * 8);
@@ -375,7 +375,7 @@ static int insert_device(flb_map* m, const float4* pts, const unsigned char* cls
     m->launches++;
   }
   if (mode == 0 || mode == 2) {
-    launch_k(k_append_points, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev);
+    launch_k(k_append_points, g, 256, 0, st, m->d, pts, c, 2, n, skip, n_dev, tail);
     m->launches++;
     // Chain relocation is a pure layout optimisation (contiguous overflow chains for the k-NN readers).  It pays after a bulk
     // verbatim insert (Build, Add_Points(false): many multi-point voxels); map_incremental's verbatim class is a few hundred
@@ -831,7 +831,7 @@ struct flb_session {
   bool device_update = true;
   EsikfScratch* d_scr = nullptr;
   cudaStream_t side = nullptr;   // second stream: k_esikf_pre overlaps the measurement kernels of the same pass
-  cudaEvent_t ev_fork[8] = {nullptr}, ev_join[8] = {nullptr};
+  cudaEvent_t ev_fork[9] = {nullptr}, ev_join[9] = {nullptr};   // one pair per pass + [8] = the posterior's publish branch
   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [0] update only, [1] update + map_incremental (no scan or host pointer baked in
   int graph_kernels[2] = {0, 0};                  //  beyond the slot's own staging / result records)
   int graph_gen = -1;            // flb_map::gen the graphs were captured at
@@ -849,7 +849,7 @@ struct flb_session {
   cudaEvent_t ev_copy = nullptr;
   int pending_n = -1;            // >= 0: a prefetched scan waits in body_alt
   // flb_scan_step_begin / _finish
-  bool step_pending = false, step_device = false;
+  bool step_pending = false, step_device = false, step_ev2 = false;
   bool flags_clean = false;      // sel / cnt hold their per-scan initial values (see scan_reset)
   int step_l0 = 0, step_deleted = 0, step_flg = 1, step_n = 0;
   double step_x[26], step_P[NDOF * NDOF];
@@ -863,7 +863,7 @@ struct flb_session {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     int gk[2] = {0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-    bool pending = false, device = false;
+    bool pending = false, device = false, ev2_on = false;
     int l0 = 0, deleted = 0, flg = 1, n = 0;
     double x[26], P[NDOF * NDOF];
   } slot[2];
@@ -874,7 +874,7 @@ struct flb_session {
 static void save_active(flb_session* s) {
   flb_session::StepSlot& o = s->slot[s->active];
   for (int i = 0; i < 2; ++i) { o.graph[i] = s->graph[i]; o.gk[i] = s->graph_kernels[i]; }
-  o.pending = s->step_pending; o.device = s->step_device; o.l0 = s->step_l0; o.deleted = s->step_deleted; o.flg = s->step_flg; o.n = s->step_n;
+  o.pending = s->step_pending; o.device = s->step_device; o.ev2_on = s->step_ev2; o.l0 = s->step_l0; o.deleted = s->step_deleted; o.flg = s->step_flg; o.n = s->step_n;
   memcpy(o.x, s->step_x, sizeof(o.x));
   memcpy(o.P, s->step_P, sizeof(o.P));
 }
@@ -885,7 +885,7 @@ static void use_slot(flb_session* s, int j) {
   s->h_x0P0 = w.h_x0P0; s->d_x0P0 = w.d_x0P0; s->h_res = w.h_res; s->d_res = w.d_res;
   for (int i = 0; i < 2; ++i) { s->graph[i] = w.graph[i]; s->graph_kernels[i] = w.gk[i]; }
   s->ev0 = w.ev0; s->ev1 = w.ev1; s->ev2 = w.ev2; s->ev3 = w.ev3;
-  s->step_pending = w.pending; s->step_device = w.device; s->step_l0 = w.l0; s->step_deleted = w.deleted; s->step_flg = w.flg; s->step_n = w.n;
+  s->step_pending = w.pending; s->step_device = w.device; s->step_ev2 = w.ev2_on; s->step_l0 = w.l0; s->step_deleted = w.deleted; s->step_flg = w.flg; s->step_n = w.n;
   memcpy(s->step_x, w.x, sizeof(w.x));
   memcpy(s->step_P, w.P, sizeof(w.P));
   s->active = j;
@@ -937,7 +937,7 @@ extern "C" int flb_session_create(flb_map* m, const flb_session_config* cfg, flb
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
-  for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
+  for (int i = 0; i < 9 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&s->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming);
   }
@@ -1015,7 +1015,7 @@ extern "C" void flb_session_destroy(flb_session* s) {
     for (cudaEvent_t e : ev) if (e) Q(cudaEventDestroy(e));
   }
   if (s->ev_copy) Q(cudaEventDestroy(s->ev_copy));
-  for (int i = 0; i < 8; ++i) { if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i])); if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i])); }
+  for (int i = 0; i < 9; ++i) { if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i])); if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i])); }
   if (s->side) Q(cudaStreamDestroy(s->side));
   if (s->copy_stream) Q(cudaStreamDestroy(s->copy_stream));
   flb_map* m = s->map;
@@ -1301,7 +1301,7 @@ static int run_update(flb_session* s, double* state26, double* P, flb_update_sta
 }
 
 
-static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl);
+static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl, bool tail_publish = false);
 
 // Device-driven scan: every pass of the iterated update (and optionally map_incremental) is enqueued up front; kernels
 // of passes that turn out not to be needed exit on the device-side loop flags.  No host round trip inside.  Launch
@@ -1364,10 +1364,23 @@ static int enqueue_scan_device(flb_session* s, bool with_insert) {
     }
   }
   CU(cudaGetLastError());
-  if (with_insert && enqueue_map_incremental(s, nullptr, 0, true)) return 1;
-  // results: one kernel writes the mapped pinned record (posterior, statistics, map counters, map_incremental's counts)
-  launch_k(k_publish, 1, 256, 0, st, (const EsikfCtl*)s->ctl, (const int*)m->d.counters, (const int*)(with_insert ? s->d_cnt2 : nullptr), s->d_res);
-  m->launches++;
+  // results go into ONE mapped pinned record (posterior, statistics, map counters, map_incremental's counts).  With an
+  // insert behind the update, the posterior is published on the side branch next to the insert kernels and the counters
+  // by the last block of the last insert kernel; otherwise one kernel writes everything.
+  const bool tail_publish = overlap && with_insert && s->cap > 0;
+  if (tail_publish) {
+    CU(cudaEventRecord(s->ev_fork[8], st));
+    CU(cudaStreamWaitEvent(s->side, s->ev_fork[8], 0));
+    k_publish<<<1, 256, 0, s->side>>>((const EsikfCtl*)s->ctl, nullptr, nullptr, s->d_res, 0);
+    CU(cudaEventRecord(s->ev_join[8], s->side));
+    m->launches++;
+  }
+  if (with_insert && enqueue_map_incremental(s, nullptr, 0, true, tail_publish)) return 1;
+  if (tail_publish) CU(cudaStreamWaitEvent(st, s->ev_join[8], 0));
+  else {
+    launch_k(k_publish, 1, 256, 0, st, (const EsikfCtl*)s->ctl, (const int*)m->d.counters, (const int*)(with_insert ? s->d_cnt2 : nullptr), s->d_res, 1);
+    m->launches++;
+  }
   CU(cudaGetLastError());
   s->have_pass = false;
   return 0;
@@ -1467,7 +1480,7 @@ extern "C" int flb_esikf_update(flb_session* s, double* state26, double* P, flb_
   return 0;
 }
 
-static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl) {
+static int enqueue_map_incremental(flb_session* s, const double* state26, int flg_EKF_inited, bool from_ctl, bool tail_publish) {
   flb_map* m = s->map;
   cudaStream_t st = m->stream;
   const int n = s->n;
@@ -1492,7 +1505,14 @@ static int enqueue_map_incremental(flb_session* s, const double* state26, int fl
   }
   CU(cudaGetLastError());
   if (from_ctl) {
-    if (insert_device(m, s->world, s->cls, s->cap, 2, &s->ctl->need_host, &s->ctl->n, true)) return 1;
+    StepTail tail{};
+    if (tail_publish) {
+      // the last block of the last insert kernel writes the map counters, map_incremental's counts and the step's device
+      // span into the mapped pinned result record: no separate publishing kernel after the insert
+      tail.ticket = s->d_cnt2 + 2; tail.counters = m->d.counters; tail.cnt2 = s->d_cnt2; tail.t_begin = &s->ctl->t_begin;
+      tail.out_counters = s->d_res->counters; tail.out_cnt2 = s->d_res->cnt2; tail.out_span = &s->d_res->span_ns;
+    }
+    if (insert_device(m, s->world, s->cls, s->cap, 2, &s->ctl->need_host, &s->ctl->n, true, tail)) return 1;
   } else if (insert_device(m, s->world, s->cls, n, 2, nullptr, nullptr, true)) return 1;
   if (!from_ctl) CU(cudaMemcpyAsync(s->h_cnt2, s->d_cnt2, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));   // (k_publish carries them otherwise)
   return 0;
@@ -1624,7 +1644,10 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
   s->step_flg = flg_EKF_inited;
   memcpy(s->step_x, state26, sizeof(s->step_x));
   memcpy(s->step_P, P, sizeof(s->step_P));
-  CU(cudaEventRecord(s->ev2, m->stream));
+  // A device-driven step without an on-stream upload times itself on the device (StepResult::span_ns): no event pair sits
+  // on the stream between two steps in flight, only the one event flb_scan_step_finish waits on.
+  s->step_ev2 = body != nullptr || !s->device_update;
+  if (s->step_ev2) CU(cudaEventRecord(s->ev2, m->stream));
   if (body) { if (flb_scan_upload(s, body, n, stride)) return 1; }
   else if (adopt_prefetched(s)) return 1;
   if (fov) {  // laserMapping.cpp:2320 (uses pos_lid of the previous posterior)
@@ -1633,11 +1656,9 @@ extern "C" int flb_scan_step_begin(flb_session* s, flb_fov_state* fov, const flo
   }
   s->step_device = s->device_update;
   if (s->step_device) {
-    CU(cudaEventRecord(s->ev0, m->stream));
     const auto hl0 = std::chrono::steady_clock::now();
     if (launch_scan_device(s, state26, P, flg_EKF_inited, true)) return 1;  // :2380 + :2401, no host round trips inside
     if (s->host_timing) s->ht_launch += std::chrono::duration<double>(std::chrono::steady_clock::now() - hl0).count();
-    CU(cudaEventRecord(s->ev1, m->stream));
     CU(cudaEventRecord(s->ev3, m->stream));
   }
   s->step_n = s->n;
@@ -1680,7 +1701,7 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
       stats_from_ctl(s->h_res, &r.update);
       s->h_cnt2[0] = s->h_res->cnt2[0];
       s->h_cnt2[1] = s->h_res->cnt2[1];
-      CU(cudaEventElapsedTime(&r.update.gpu_ms, s->ev0, s->ev1));
+      r.update.gpu_ms = (float)((double)s->h_res->span_ns * 1e-6);
     }
   }
   if (host_path) {
@@ -1699,7 +1720,8 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
   r.n_to_add = s->step_n > 0 ? s->h_cnt2[0] : 0;
   r.n_no_downsample = s->step_n > 0 ? s->h_cnt2[1] : 0;
   r.map_valid = m->h_counters[CNT_VALID];
-  CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
+  if (s->step_ev2) CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
+  else r.gpu_ms_total = r.update.gpu_ms;
   r.kernel_launches = s->step_l0 + (m->launches - launches0);
   if (out) *out = r;
   const int rrc = maybe_rehash(m);

@@ -170,6 +170,7 @@ struct EsikfCtl {
   int flg_inited;      // flg_EKF_inited of this scan (laserMapping.cpp:2317)
   int pad_;
   const float4* body;  // feats_down_body of this scan (travels with the staged inputs: the captured graphs do not depend on it)
+  unsigned long long t_begin;   // %globaltimer when this scan's sequence started (k_esikf_begin); k_publish reports the span
 };
 __device__ __forceinline__ bool ctl_pass_active(const EsikfCtl* c) { return !c->finished && c->it < c->max_iter; }
 
@@ -613,6 +614,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_CTAS) k_knn(KnnArgs a) {
       const long long e1 = clock64();
       FLB_DBG_ADD(16, 1); FLB_DBG_ADD(17, e1 - e0); FLB_DBG_MAX(18, e1 - e0); FLB_DBG_ADD(18 + min(dbg_rings, 6), 1);
       FLB_DBG_ADD(25, done ? 0 : 1);
+      FLB_DBG_ADD(58 + (int)min((e1 - e0) >> 13, 5ll), 1);   // histogram of the per-query cycles, 8192-cycle buckets
       FLB_DBG_ADD(32, ph_seed); FLB_DBG_ADD(33, ph_probe); FLB_DBG_ADD(36, ph_merge);
     }
 #endif
@@ -823,6 +825,9 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
   TopKId<K> t;
   t.clear();
   bool done = false;
+  FLB_DBG_CLOCK(w0);
+  bool dbg_fallback = false;
+  (void)dbg_fallback;
   if (fabsf(qx) < qlim && fabsf(qy) < qlim && fabsf(qz) < qlim) {
     const int cvx = voxel_of(qx, ds), cvy = voxel_of(qy, ds), cvz = voxel_of(qz, ds);
     const int bbx = (cvx - 2) >> 2, bby = (cvy - 2) >> 2, bbz = (cvz - 2) >> 2;
@@ -879,8 +884,26 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
     stencil_pass<K, false>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);
-    if (!stencil_shell_pass<K>(m, sm, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain))
+    if (!stencil_shell_pass<K>(m, sm, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain)) {
       stencil_pass<K, true>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);  // no bound / list overflow: the whole shell
+      dbg_fallback = true;
+    }
+#ifdef FLB_TRACE
+    if (a.ctl && a.ctl->it + 1 == 0) {   // first search pass: how the warps' durations spread (the kernel lasts as long as its slowest warp)
+      const unsigned act = __activemask();
+      const long long w1 = clock64();
+      const int nfb = __popc(__ballot_sync(act, dbg_fallback));
+      int mxc = n_chain + n_head;
+      for (int o = 16; o; o >>= 1) mxc = max(mxc, __shfl_xor_sync(act, mxc, o));
+      if ((tid & 31) == __ffs(act) - 1) {
+        const long long d = w1 - w0;
+        FLB_DBG_ADD(40, 1); FLB_DBG_ADD(41, d); FLB_DBG_MAX(42, d);
+        if (nfb) { FLB_DBG_ADD(43, 1); FLB_DBG_ADD(44, d); FLB_DBG_ADD(45, nfb); }
+        FLB_DBG_ADD(48 + (int)min(d >> 13, 7ll), 1);          // histogram, 8192-cycle buckets
+        FLB_DBG_ADD(56, mxc); FLB_DBG_MAX(57, mxc);
+      }
+    }
+#endif
     if (a.phase_stats) {  // profiling only: candidate statistics
       atomicAdd(&a.phase_stats[4], n_chain);
       atomicMax(&a.phase_stats[5], n_chain);

@@ -133,12 +133,26 @@ __global__ void k_touch_blocks(MapDev m, const float4* __restrict__ pts, const u
 
 // ---------------------------------------------------------------------------------------------- K3b: verbatim append
 // Add_Points(..., downsample_on=false) (ikd_Tree.cpp:471-472) and Build (ikd_Tree.cpp:352-364): no dedupe.
+// Optional epilogue of the LAST kernel of a captured scan sequence: the block that finishes last copies the map counters,
+// map_incremental's two counts and the sequence's device span into the (mapped pinned) result record, so that no separate
+// publishing kernel — one more launch gap on the critical path between two scans — follows the insert.
+struct StepTail {
+  int* ticket = nullptr;                         // zero before the launch; the last block leaves it zero again
+  const int* counters = nullptr;                 // [32] map counters
+  const int* cnt2 = nullptr;                     // [2] map_incremental's counts
+  const unsigned long long* t_begin = nullptr;   // %globaltimer at the start of the sequence
+  int* out_counters = nullptr;
+  int* out_cnt2 = nullptr;
+  unsigned long long* out_span = nullptr;
+};
+
 __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const unsigned char* __restrict__ cls,
-                                int want_cls, int n, const int* __restrict__ skip, const int* __restrict__ n_dev) {
+                                int want_cls, int n, const int* __restrict__ skip, const int* __restrict__ n_dev, StepTail tail) {
   pdl_sync();
   FLB_TRACE_BEGIN(10 * 8);
-  if (skip && *skip) return;
+  const bool skipped = skip && *skip;
   if (n_dev) n = *n_dev;
+  if (skipped) n = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (cls && cls[i] != want_cls) continue;
     const float4 p = pts[i];
@@ -166,6 +180,22 @@ __global__ void k_append_points(MapDev m, const float4* __restrict__ pts, const 
     atomicAdd(&m.counters[CNT_VALID], 1);
   }
   FLB_TRACE_END(10 * 8);
+  if (tail.ticket) {
+    __shared__ int s_last;
+    __syncthreads();                       // every counter update of this block has been issued
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(tail.ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {                          // block-uniform
+      __threadfence();
+      if (threadIdx.x < 32) tail.out_counters[threadIdx.x] = __ldcg(&tail.counters[threadIdx.x]);
+      else if (threadIdx.x < 34) tail.out_cnt2[threadIdx.x - 32] = __ldcg(&tail.cnt2[threadIdx.x - 32]);
+      else if (threadIdx.x == 34) *tail.out_span = global_timer_ns() - __ldcg(tail.t_begin);
+      else if (threadIdx.x == 35) *tail.ticket = 0;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- K3b': chain relocation

@@ -35,6 +35,11 @@ namespace flb {
 // the stream / graph instead of starting only after it has drained.  Every such kernel calls this first: it blocks
 // until ALL prerequisite grids have completed and their memory is visible (so nothing below it can see stale data), and
 // then allows its own dependents to be scheduled.  A no-op for kernels launched the ordinary way.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

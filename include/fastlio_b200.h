@@ -178,7 +178,8 @@ int flb_pass_rows(flb_session* s, double* h_x_colmajor, int ld, double* h, int c
 typedef struct flb_update_stats {
   int passes, search_passes, effct_feat_num, converged_count;
   double total_residual;
-  float gpu_ms;            /* CUDA-event time of all kernels of this update */
+  float gpu_ms;            /* device time of all kernels of this update (CUDA events; inside flb_scan_step: the sequence's own
+                              %globaltimer span, update + insert) */
 } flb_update_stats;
 
 /* update_iterated_dyn_share_modified (esekfom.hpp:1620-1938) with the built-in measurement model: state26 / P23x23
@@ -219,7 +220,8 @@ int flb_fov_segment(flb_map* m, flb_fov_state* fov, const double* pos_lid, float
 typedef struct flb_scan_result {
   flb_update_stats update;
   int n_to_add, n_no_downsample, n_deleted, map_valid;
-  float gpu_ms_total;      /* update + insert + delete kernels, CUDA events on the session stream */
+  float gpu_ms_total;      /* update + insert kernels (+ the on-stream upload and the box deletes when `body` is passed: CUDA
+                              events then; otherwise the device-side span of the step's sequence) */
   int kernel_launches;     /* number of kernels launched by this step */
 } flb_scan_result;
 /* The timed region of SURVEY.md §8d: lasermap_fov_segment -> update_iterated_dyn_share_modified -> map_incremental

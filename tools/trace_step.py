@@ -67,6 +67,7 @@ def main():
     L.flb_debug_trace_read(tr, ph, dbg)
     rows = {}
     phases = {}
+    pre_ph = []
     total = []
     for k in range(args.warmup, n_scans):
         step(k)
@@ -88,7 +89,9 @@ def main():
                 last = max(last, b - t0)
         total.append(last * 1e-3)
         p = np.array(ph, dtype=np.int64).reshape(8, 12)
-        for pas in range(8):
+        if p[6, 0] and p[6, 6]:
+            pre_ph.append([p[6, j] - p[6, 0] for j in range(7)])
+        for pas in range(1, 5):
             if p[pas, 0] and p[pas, 6]:
                 phases.setdefault(pas, []).append([(p[pas, j] - p[pas, 0]) if p[pas, j] else -1 for j in range(7)])
     out = {"steps": args.steps, "timeline_us": [], "post_phases_cycles": {}, "last_kernel_end_us_mean": float(np.mean(total))}
@@ -108,6 +111,11 @@ def main():
         m = np.mean(np.array(phases[pas], dtype=np.float64), axis=0)
         print(f"pass {pas}: " + ", ".join(f"{PHASES[j]}={m[j]:.0f}" for j in range(1, 7)))
         out["post_phases_cycles"][str(pas)] = {PHASES[j]: float(m[j]) for j in range(1, 7)}
+    if pre_ph:
+        m = np.mean(np.array(pre_ph, dtype=np.float64), axis=0)
+        names = ["", "state / covariance staged", "boxminus + Jacobians", "covariance projected", "projection stored", "inverse", "Q written"]
+        print("# k_esikf_pre, pass 1 (clock cycles after kernel start, thread 0): " + ", ".join(f"{names[j]}={m[j]:.0f}" for j in range(1, 7)))
+        out["pre_phases_cycles"] = {names[j]: float(m[j]) for j in range(1, 7)}
     S = args.steps
     if dbg_sum[16] > 0:
         nq = dbg_sum[16]
@@ -115,10 +123,18 @@ def main():
               f"queries/step={nq / S:.0f} cycles/query={dbg_sum[17] / nq:.0f} max={dbg_max[18]:.0f} "
               f"done after ring1/2/3={dbg_sum[19] / nq:.3f}/{dbg_sum[20] / nq:.3f}/{dbg_sum[21] / nq:.3f} coarse={dbg_sum[25] / nq:.4f} "
               "")
+        print("# exact kernel, first pass: share of queries by duration (8192-cycle buckets): " + " ".join(f"{dbg_sum[58 + j] / nq:.3f}" for j in range(6)))
         if dbg_sum[32] > 0:
             print("# exact kernel, cycles/query by phase: " + ", ".join(
                 f"{nm}={dbg_sum[i] / nq:.0f}" for nm, i in (("ticket", 32), ("seed loads + block batches (probes, compaction, point loads)", 33),
                                                             ("merges", 36))))
+    if dbg_sum[40] > 0:
+        nw = dbg_sum[40]
+        print(f"# stencil kernel, first pass: warps/step={nw / S:.0f} mean cycles/warp={dbg_sum[41] / nw:.0f} max={dbg_max[42]:.0f}; "
+              f"warps with a whole-shell lane={dbg_sum[43] / nw:.3f} (mean cycles {dbg_sum[44] / max(dbg_sum[43], 1):.0f}, "
+              f"{dbg_sum[45] / max(dbg_sum[43], 1):.1f} such lanes each); largest per-lane candidate count of a warp: mean={dbg_sum[56] / nw:.1f} max={dbg_max[57]:.0f}")
+        print("# stencil kernel, first pass: share of warps by duration (8192-cycle buckets): " +
+              " ".join(f"{dbg_sum[48 + j] / nw:.3f}" for j in range(8)))
     if args.pairs > 0:
         # two steps in flight: device time from the first kernel of step k to the last kernel of step k+1, against twice the
         # single-step span -> what the device loses BETWEEN two graph launches (copies, graph start-up)
