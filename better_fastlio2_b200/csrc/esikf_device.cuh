@@ -280,6 +280,47 @@ __device__ __forceinline__ void b_mul_cols_T(double* M, int idx, const double* J
   if (tid < NDOF) for (int j = 0; j < D; ++j) M[tid * NDOF + idx + j] = t[j];
   __syncthreads();
 }
+// ---- the three projected sub-manifolds together.  The projection Jacobian of esekfom.hpp:1665-1703 / :1841-1918 is block
+// diagonal: identity except J3a on rows/cols 3..5 (rot), J3b on 6..8 (offset_R_L_I) and J2 on 21..22 (grav).  The blocks touch
+// disjoint rows (columns), so all row products form ONE phase and all column products another: 8 x 23 outputs per phase,
+// one per thread, instead of six block-wide phases of 23 busy threads each.  (Entries that sit in the rows of one block and
+// the columns of another see "rows, then columns" instead of the reference's block-by-block order: the same products in
+// another association, a rounding-level difference.)
+struct ProjSel { const double* J; int idx, D, i; };
+__device__ __forceinline__ ProjSel proj_sel(int o, const double* J3a, const double* J3b, const double* J2) {
+  ProjSel r;
+  if (o < 3) { r.J = J3a; r.idx = 3; r.D = 3; r.i = o; }
+  else if (o < 6) { r.J = J3b; r.idx = 6; r.D = 3; r.i = o - 3; }
+  else { r.J = J2; r.idx = 21; r.D = 2; r.i = o - 6; }
+  return r;
+}
+// value of (J Src)[row of output o][c]
+__device__ __forceinline__ double proj_row_value(const double* Src, int ld, const ProjSel& q, int c) {
+  double s = 0;
+  for (int k = 0; k < q.D; ++k) s += q.J[q.D * q.i + k] * Src[(q.idx + k) * ld + c];
+  return s;
+}
+// value of (M J^T)[r][column of output o]
+__device__ __forceinline__ double proj_col_value(const double* M, const ProjSel& q, int r) {
+  double s = 0;
+  for (int k = 0; k < q.D; ++k) s += M[r * NDOF + q.idx + k] * q.J[q.D * q.i + k];
+  return s;
+}
+constexpr int PROJ_OUT = 8 * NDOF;   // 184 outputs per phase
+// M <- Jfull M Jfull^T in place (every thread of the block calls it)
+__device__ __forceinline__ void b_project(double* M, const double* J3a, const double* J3b, const double* J2, int tid) {
+  const int o = tid / NDOF, c = tid - o * NDOF;
+  ProjSel q = proj_sel(o < 8 ? o : 0, J3a, J3b, J2);
+  double v = 0;
+  if (tid < PROJ_OUT) v = proj_row_value(M, NDOF, q, c);
+  __syncthreads();
+  if (tid < PROJ_OUT) M[(q.idx + q.i) * NDOF + c] = v;
+  __syncthreads();
+  if (tid < PROJ_OUT) v = proj_col_value(M, q, c);        // c = row index here
+  __syncthreads();
+  if (tid < PROJ_OUT) M[c * NDOF + q.idx + q.i] = v;
+  __syncthreads();
+}
 // Inverse of A (23x23) by Gauss-Jordan with partial pivoting on aug = [A | I] (23 x 46), ping-pong buffered so that one
 // pivot step = ONE barrier: every warp finds the pivot row redundantly (shuffles, first maximum wins), then each
 // thread writes new[r][j] from old values only:  row c <- old[piv]/pivot ;  other rows <- old[src] - old[src][c]*row c
@@ -416,10 +457,17 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
   const int trace_ph = c->it + 1 == 1 ? 72 : 1 << 20;   // phases of the pass-1 launch (normally a pass without a search: this kernel is its critical path)
   (void)trace_slot; (void)trace_ph;
   FLB_TRACE_PHASE(trace_ph + 0);
-  if (c->finished || c->it >= c->max_iter || c->n <= 0) return;   // uniform
-  if (tid >= 32 && tid < 58) { xs[tid - 32] = c->x[tid - 32]; xps[tid - 32] = c->xp[tid - 32]; }
-  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) P[e] = c->Pp[e];
+  // the loads are issued ahead of the loop flags and complete under them
+  double pP[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) { const int e = tid + u * ESIKF_THREADS; pP[u] = e < NDOF * NDOF ? c->Pp[e] : 0.0; }
+  double px = 0.0, pxp = 0.0;
+  if (tid >= 32 && tid < 58) { px = c->x[tid - 32]; pxp = c->xp[tid - 32]; }
   const double R = c->R;
+  if (c->finished || c->it >= c->max_iter || c->n <= 0) return;   // uniform
+  if (tid >= 32 && tid < 58) { xs[tid - 32] = px; xps[tid - 32] = pxp; }
+#pragma unroll
+  for (int u = 0; u < 3; ++u) { const int e = tid + u * ESIKF_THREADS; if (e < NDOF * NDOF) P[e] = pP[u]; }
   __syncthreads();
   FLB_TRACE_PHASE(trace_ph + 1);   // state / covariance staged
   // x_ [-] x_propagated (:1655) and the projection Jacobians, one sub-manifold per warp
@@ -451,12 +499,7 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
     else if (tid >= 21) { const int i = tid - 21; v = J2[2 * i] * dx[21] + J2[2 * i + 1] * dx[22]; }
     sc->dxn[tid] = v;
   }
-  b_mul_rows<3>(P, P, 3, J3a, tid);                     // SO3 blocks :1665-1681
-  b_mul_cols_T<3>(P, 3, J3a, tid);
-  b_mul_rows<3>(P, P, 6, J3b, tid);
-  b_mul_cols_T<3>(P, 6, J3b, tid);
-  b_mul_rows<2>(P, P, 21, J2, tid);                     // S2 block :1683-1703
-  b_mul_cols_T<2>(P, 21, J2, tid);
+  b_project(P, J3a, J3b, J2, tid);                      // SO3 blocks :1665-1681, S2 block :1683-1703
   FLB_TRACE_PHASE(trace_ph + 3);   // covariance projected
   for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) sc->P[e] = P[e];
   if (tid < MD * MD) L[tid] = P[(tid / MD) * NDOF + (tid % MD)] / R;   // Pr11 (MD x MD)
@@ -468,8 +511,8 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_pre(const EsikfCtl
   for (int e = tid; e < NDOF * MD; e += ESIKF_THREADS) {               // Q = Pr[:, 0:MD] T11
     const int i = e / MD, j = e - i * MD;
     double q = 0;
-    for (int k = 0; k < MD; ++k) q += (P[i * NDOF + k] / R) * T11[k * MD + j];
-    sc->Q[e] = q;
+    for (int k = 0; k < MD; ++k) q += P[i * NDOF + k] * T11[k * MD + j];
+    sc->Q[e] = q / R;                                                  // (one division per entry: sum(P T11) / R)
   }
   FLB_TRACE_PHASE(trace_ph + 6);   // Q written
   FLB_TRACE_END(trace_slot);
@@ -635,29 +678,27 @@ __global__ void __launch_bounds__(dev::ESIKF_THREADS) k_esikf_post(EsikfCtl* c, 
   __syncthreads();
   const int fin = s_fin;
   FLB_TRACE_PHASE(trace_pass * 12 + 5);   // boxplus (+ final Jacobians) done
-  if (fin) {                                            // :1841-1931
-    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) L[e] = P[e];
-    __syncthreads();
-    for (int b = 0; b < 2; ++b) {
-      const int idx = b == 0 ? 3 : 6;
-      const double* J3 = b == 0 ? J3a : J3b;
-      b_mul_rows<3>(L, P, idx, J3, tid);
-      double tv[3];
-      if (tid < 12) for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += J3[3 * i + k] * Kx[(idx + k) * 12 + tid]; tv[i] = s; }
-      __syncthreads();
-      if (tid < 12) for (int i = 0; i < 3; ++i) Kx[(idx + i) * 12 + tid] = tv[i];
-      __syncthreads();
-      b_mul_cols_T<3>(L, idx, J3, tid);
-      b_mul_cols_T<3>(P, idx, J3, tid);
+  if (fin) {                                            // :1841-1931, the three sub-manifold blocks together (see b_project)
+    // L = Jfull P (rows; L is a separate buffer: no staging), K_x rows <- Jfull K_x rows (in place: staged in registers)
+    const int o = tid / NDOF, cc = tid - o * NDOF;
+    const ProjSel q = proj_sel(o < 8 ? o : 0, J3a, J3b, J2);
+    for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) {
+      const int r = e / NDOF;
+      if (!((r >= 3 && r < 9) || r >= 21)) L[e] = P[e];
     }
-    b_mul_rows<2>(L, P, 21, J2, tid);
-    double a0 = 0, a1 = 0;
-    if (tid < 12) { a0 = J2[0] * Kx[21 * 12 + tid] + J2[1] * Kx[22 * 12 + tid]; a1 = J2[2] * Kx[21 * 12 + tid] + J2[3] * Kx[22 * 12 + tid]; }
+    if (tid < PROJ_OUT) L[(q.idx + q.i) * NDOF + cc] = proj_row_value(P, NDOF, q, cc);
+    const int ok = tid / 12, ck = tid - ok * 12;                    // 8 x 12 outputs of the gain
+    const ProjSel qk = proj_sel(ok < 8 ? ok : 0, J3a, J3b, J2);
+    double kv = 0;
+    if (tid < 96) kv = proj_row_value(Kx, 12, qk, ck);
     __syncthreads();
-    if (tid < 12) { Kx[21 * 12 + tid] = a0; Kx[22 * 12 + tid] = a1; }
+    if (tid < 96) Kx[(qk.idx + qk.i) * 12 + ck] = kv;
+    // columns of L and of P (in place, staged in registers)
+    double lv = 0, pv = 0;
+    if (tid < PROJ_OUT) { lv = proj_col_value(L, q, cc); pv = proj_col_value(P, q, cc); }
     __syncthreads();
-    b_mul_cols_T<2>(L, 21, J2, tid);
-    b_mul_cols_T<2>(P, 21, J2, tid);
+    if (tid < PROJ_OUT) { L[cc * NDOF + q.idx + q.i] = lv; P[cc * NDOF + q.idx + q.i] = pv; }
+    __syncthreads();
     for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) {      // P_ = L_ - K_x[:, :12] P_[:12, :]
       const int i = e / NDOF, j = e - i * NDOF;
       double s = 0;

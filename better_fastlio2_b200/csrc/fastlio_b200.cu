@@ -1015,7 +1015,10 @@ extern "C" void flb_session_destroy(flb_session* s) {
     for (cudaEvent_t e : ev) if (e) Q(cudaEventDestroy(e));
   }
   if (s->ev_copy) Q(cudaEventDestroy(s->ev_copy));
-  for (int i = 0; i < 9; ++i) { if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i])); if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i])); }
+  for (int i = 0; i < 9; ++i) {
+    if (s->ev_fork[i]) Q(cudaEventDestroy(s->ev_fork[i]));
+    if (s->ev_join[i]) Q(cudaEventDestroy(s->ev_join[i]));
+  }
   if (s->side) Q(cudaStreamDestroy(s->side));
   if (s->copy_stream) Q(cudaStreamDestroy(s->copy_stream));
   flb_map* m = s->map;

@@ -740,71 +740,86 @@ __device__ __forceinline__ void stencil_pass(const MapDev& m, const StencilSmem&
 // to the query exceeds the k-th distance are dropped (15 compares), the three 5-bit slab masks are expanded to the 8
 // blocks with the separable mask builder, and only the occupied voxels inside that box go through (1) a flat, load-free
 // loop that applies the exact box lower bound (sum of the three gaps) and compacts the survivors into a small per-thread
-// list — lanes only diverge on cheap code — and (2) the loads, four survivors at a time.  Returns false if the list
-// overflowed (no k-th distance yet, sparse surroundings: the caller then visits the whole shell).
+// list — lanes only diverge on cheap code — and (2) the loads, four survivors at a time; a full list is drained and the
+// walk resumes with the tighter k-th distance.
 // (ncu source view, round 1: walking all ~60 occupied shell voxels per query one by one was 30 % of the kernel's instructions.)
 template <int K>
-__device__ __forceinline__ bool stencil_shell_pass(const MapDev& m, StencilSmem& sm, int tid, int ox, int oy, int oz, float qx,
+__device__ __forceinline__ void stencil_shell_pass(const MapDev& m, StencilSmem& sm, int tid, int ox, int oy, int oz, float qx,
                                                    float qy, float qz, float lim, TopKId<K>& t, int& n_head, int& n_chain) {
-  const float bound = t.d[K - 1];
-  if (!(bound < CUDART_INF_F)) return false;   // nothing to prune with
+  // (no k-th distance yet = fewer than K points in the inner 3x3x3, sparse surroundings: bound = INF keeps every slab and
+  // every occupied shell voxel — usually a short list — and the lane stays on the path of its warp's other lanes instead of
+  // adding a whole-shell loop as a third divergent phase: those warps were the kernel's tail, 59k vs 37k cycles)
   unsigned wx = 0u, wy = 0u, wz = 0u;
+  {
+    const float bound0 = t.d[K - 1];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    wx |= (sm.gap[j][tid] <= bound) ? (1u << j) : 0u;
-    wy |= (sm.gap[5 + j][tid] <= bound) ? (1u << j) : 0u;
-    wz |= (sm.gap[10 + j][tid] <= bound) ? (1u << j) : 0u;
+    for (int j = 0; j < 5; ++j) {
+      wx |= (sm.gap[j][tid] <= bound0) ? (1u << j) : 0u;
+      wy |= (sm.gap[5 + j][tid] <= bound0) ? (1u << j) : 0u;
+      wz |= (sm.gap[10 + j][tid] <= bound0) ? (1u << j) : 0u;
+    }
   }
   const unsigned ax = wx << ox, ay = wy << oy, az = wz << oz;   // 8-bit masks over the two blocks per axis
-  int ns = 0;
+  // fill the list (load-free, cut with the k-th distance SO FAR), drain it (loads + insertions), and go on where the fill
+  // stopped if the list was full: a dense shell under a loose bound streams through the same 32 entries, each round with a
+  // tighter bound, instead of overflowing into an unpruned walk over all 98 voxels
+  int b = 0;
+  unsigned long long cand = 0ull;
+  bool more = true;
 #pragma unroll 1
-  for (int b = 0; b < 8; ++b) {
-    unsigned long long cand = sm.c5[b][tid] & stencil_mask(ax, ay, az, b);
-    if (cand == 0ull) continue;
-    cand &= ~inner_mask(sm, tid, b);
-    while (cand != 0ull) {
+  while (more) {
+    const float bound = t.d[K - 1];
+    int ns = 0;
+#pragma unroll 1
+    while (ns < SHELL_LIST) {
+      if (cand == 0ull) {
+        if (b == 8) { more = false; break; }
+        cand = sm.c5[b][tid] & stencil_mask(ax, ay, az, b);
+        if (cand != 0ull) cand &= ~inner_mask(sm, tid, b);
+        ++b;
+        continue;
+      }
       const int sl = __ffsll((long long)cand) - 1;
       cand &= cand - 1;
+      const int bb = b - 1;
       // stencil-relative voxel index per axis (0..4): block half * 4 + local coordinate - stencil origin
-      const int jx = ((b & 1) << 2) + (sl & 3) - ox, jy = (((b >> 1) & 1) << 2) + ((sl >> 2) & 3) - oy, jz = ((b >> 2) << 2) + (sl >> 4) - oz;
+      const int jx = ((bb & 1) << 2) + (sl & 3) - ox, jy = (((bb >> 1) & 1) << 2) + ((sl >> 2) & 3) - oy, jz = ((bb >> 2) << 2) + (sl >> 4) - oz;
       const float md = sm.gap[jx][tid] + sm.gap[5 + jy][tid] + sm.gap[10 + jz][tid];
       if (!(md > bound)) {  // a point of this voxel could still enter the top-K
-        if (ns < SHELL_LIST) sm.list[ns][tid] = (unsigned char)(jx + 5 * jy + 25 * jz);
+        sm.list[ns][tid] = (unsigned char)(jx + 5 * jy + 25 * jz);
         ++ns;
       }
     }
-  }
-  if (ns > SHELL_LIST) return false;
-  for (int base = 0; base < ns; base += 4) {
-    unsigned pid[4];
-    float4 e[4];
+    for (int base = 0; base < ns; base += 4) {
+      unsigned pid[4];
+      float4 e[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      pid[u] = 0u;
-      if (base + u < ns) {
-        const int j = sm.list[base + u][tid];
-        const int jz = j / 25, r = j - 25 * jz, jy = r / 5, jx = r - 5 * jy;
-        const int vx = ox + jx, vy = oy + jy, vz = oz + jz;   // 0..7 across the two blocks per axis
-        const int b = (vx >> 2) | ((vy >> 2) << 1) | ((vz >> 2) << 2);
-        pid[u] = (unsigned)sm.blk[b][tid] * 64u + (unsigned)((vx & 3) | ((vy & 3) << 2) | ((vz & 3) << 4));
-        e[u] = __ldg(&m.slots[pid[u]]);
+      for (int u = 0; u < 4; ++u) {
+        pid[u] = 0u;
+        if (base + u < ns) {
+          const int j = sm.list[base + u][tid];
+          const int jz = j / 25, r = j - 25 * jz, jy = r / 5, jx = r - 5 * jy;
+          const int vx = ox + jx, vy = oy + jy, vz = oz + jz;   // 0..7 across the two blocks per axis
+          const int vb = (vx >> 2) | ((vy >> 2) << 1) | ((vz >> 2) << 2);
+          pid[u] = (unsigned)sm.blk[vb][tid] * 64u + (unsigned)((vx & 3) | ((vy & 3) << 2) | ((vz & 3) << 4));
+          e[u] = __ldg(&m.slots[pid[u]]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (base + u < ns) {
+          float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
+          if (dd <= lim && dd < t.d[K - 1]) t.insert(dd, pid[u]);
+          ++n_head;
+          walk_chain(m, __float_as_int(e[u].w), [&](const float4 o, int c) {  // overflow chain of this voxel
+            ++n_chain;
+            const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
+            if (d2 <= lim && d2 < t.d[K - 1]) t.insert(d2, 0x80000000u | (unsigned)c);
+          });
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (base + u < ns) {
-        float dd = sqdist(qx, qy, qz, e[u].x, e[u].y, e[u].z);
-        if (dd <= lim && dd < t.d[K - 1]) t.insert(dd, pid[u]);
-        ++n_head;
-        walk_chain(m, __float_as_int(e[u].w), [&](const float4 o, int c) {  // overflow chain of this voxel
-          ++n_chain;
-          const float d2 = sqdist(qx, qy, qz, o.x, o.y, o.z);
-          if (d2 <= lim && d2 < t.d[K - 1]) t.insert(d2, 0x80000000u | (unsigned)c);
-        });
-      }
-    }
   }
-  return true;
 }
 
 template <int K>
@@ -884,10 +899,7 @@ __global__ void __launch_bounds__(STENCIL_THREADS, 7) k_knn_stencil(KnnArgs a) {
     // ---- inner 3x3x3 first (gives a tight k-th distance), then the outer shell with box-distance pruning
     int n_chain = 0, n_head = 0;
     stencil_pass<K, false>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);
-    if (!stencil_shell_pass<K>(m, sm, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain)) {
-      stencil_pass<K, true>(m, sm, tid, ix, iy, iz, qx, qy, qz, lim, t, n_head, n_chain);  // no bound / list overflow: the whole shell
-      dbg_fallback = true;
-    }
+    stencil_shell_pass<K>(m, sm, tid, ox, oy, oz, qx, qy, qz, lim, t, n_head, n_chain);
 #ifdef FLB_TRACE
     if (a.ctl && a.ctl->it + 1 == 0) {   // first search pass: how the warps' durations spread (the kernel lasts as long as its slowest warp)
       const unsigned act = __activemask();

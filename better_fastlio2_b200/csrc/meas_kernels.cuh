@@ -281,9 +281,9 @@ __global__ void __launch_bounds__(MEAS_THREADS) k_residual(MeasArgs a) {
   int msum = 0;
   FLB_TRACE_BEGIN(4 * 8 + (a.ctl ? a.ctl->it + 1 : 0));
   if (a.ctl && !ctl_pass_active(a.ctl)) return;   // the iterated update already finished (block-uniform)
+  const int search = a.ctl ? a.ctl->converge : a.search;
   const PoseDev pose = a.ctl ? a.ctl->pose : a.pose;
   const float4* __restrict__ body = a.ctl ? a.ctl->body : a.body;
-  const int search = a.ctl ? a.ctl->converge : a.search;
   const int n = a.ctl ? a.ctl->n : a.n;
   const int stride = gridDim.x * blockDim.x;
   const int nround = (n + stride - 1) / stride;
