@@ -141,79 +141,8 @@ __device__ __noinline__ double* b_inverse_spd(double* buf0, double* buf1, int ti
   return cur;
 }
 
-// J (2x2) = Nx_yy(xg) * Mx(xpg, delta)   (S2.hpp:259-280, esekfom.hpp:1693-1695)
-__device__ __forceinline__ void s2_jac(const double* xg, const double* xpg, const double* delta, double* J) {
-  const double len = 98090.0 / 10000.0;
-  double Bx[6], H[9], Nx[6];
-  s2_Bx(xg, Bx);
-  hat(xg, H);
-  const double sc = 1 / len / len;
-  for (int i = 0; i < 2; ++i)
-    for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += (sc * Bx[2 * k + i]) * H[3 * k + j]; Nx[3 * i + j] = s; }
-  double Bp[6], Hp[9], Mx[6];
-  s2_Bx(xpg, Bp);
-  hat(xpg, Hp);
-  const double dn = sqrt(delta[0] * delta[0] + delta[1] * delta[1]);
-  if (dn < 1e-11) {
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += (-Hp[3 * i + k]) * Bp[2 * k + j]; Mx[2 * i + j] = s; }
-  } else {
-    double Bu[3];
-    for (int i = 0; i < 3; ++i) Bu[i] = Bp[2 * i] * delta[0] + Bp[2 * i + 1] * delta[1];
-    double q[4], E[9], At[9], T1[9], T2[9];
-    exp_quat(Bu, 0.0, q);  // scalar(1/2) == 0 in the reference (S2.hpp:277)
-    rotmat(q, E);
-    A_matrix_T(Bu, At);
-    for (int i = 0; i < 9; ++i) E[i] = -E[i];
-    mm3(E, Hp, T1);
-    mm3(T1, At, T2);
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += T2[3 * i + k] * Bp[2 * k + j]; Mx[2 * i + j] = s; }
-  }
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += Nx[3 * i + k] * Mx[2 * k + j]; J[2 * i + j] = s; }
-}
-__device__ __forceinline__ void state_boxplus(double* x, const double* d) {  // build_manifold.hpp:188-190
-  for (int i = 0; i < 3; ++i) x[i] += d[i];
-  double q[4];
-  exp_quat(d + 3, 0.5, q); qmul(x + 3, q, x + 3);
-  exp_quat(d + 6, 0.5, q); qmul(x + 7, q, x + 7);
-  for (int i = 0; i < 3; ++i) { x[11 + i] += d[9 + i]; x[14 + i] += d[12 + i]; x[17 + i] += d[15 + i]; x[20 + i] += d[18 + i]; }
-  double Bx[6], Bu[3], R[9], o[3];
-  s2_Bx(x + 23, Bx);
-  for (int i = 0; i < 3; ++i) Bu[i] = Bx[2 * i] * d[21] + Bx[2 * i + 1] * d[22];
-  exp_quat(Bu, 0.5, q);
-  rotmat(q, R);
-  for (int i = 0; i < 3; ++i) o[i] = R[3 * i] * x[23] + R[3 * i + 1] * x[24] + R[3 * i + 2] * x[25];
-  x[23] = o[0]; x[24] = o[1]; x[25] = o[2];
-}
-__device__ __forceinline__ void state_boxminus(const double* x, const double* o, double* r) {  // x [-] o
-  for (int i = 0; i < 3; ++i) r[i] = x[i] - o[i];
-  double qc[4], q[4];
-  qc[0] = -o[3]; qc[1] = -o[4]; qc[2] = -o[5]; qc[3] = o[6];
-  qmul(qc, x + 3, q); log_quat(q, r + 3);
-  qc[0] = -o[7]; qc[1] = -o[8]; qc[2] = -o[9]; qc[3] = o[10];
-  qmul(qc, x + 7, q); log_quat(q, r + 6);
-  for (int i = 0; i < 3; ++i) { r[9 + i] = x[11 + i] - o[11 + i]; r[12 + i] = x[14 + i] - o[14 + i]; r[15 + i] = x[17 + i] - o[17 + i]; r[18 + i] = x[20 + i] - o[20 + i]; }
-  // S2 boxminus (S2.hpp:144-167): this = x.grav, other = o.grav
-  const double* v = x + 23;
-  const double* ov = o + 23;
-  double H[9], t[3];
-  hat(v, H);
-  for (int i = 0; i < 3; ++i) t[i] = H[3 * i] * ov[0] + H[3 * i + 1] * ov[1] + H[3 * i + 2] * ov[2];
-  const double v_sin = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-  const double v_cos = v[0] * ov[0] + v[1] * ov[1] + v[2] * ov[2];
-  const double theta = atan2(v_sin, v_cos);
-  if (v_sin < 1e-11) {
-    r[21] = fabs(theta) > 1e-11 ? 3.1415926 : 0.0;
-    r[22] = 0.0;
-  } else {
-    double Bx[6], Ho[9], u[3];
-    s2_Bx(ov, Bx);
-    hat(ov, Ho);
-    for (int i = 0; i < 3; ++i) u[i] = Ho[3 * i] * v[0] + Ho[3 * i + 1] * v[1] + Ho[3 * i + 2] * v[2];
-    const double f = theta / v_sin;
-    for (int i = 0; i < 2; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += (f * Bx[2 * k + i]) * u[k]; r[21 + i] = s; }
-  }
-}
-// ---- piecewise versions so that independent sub-manifolds are handled by different warps concurrently
+// ---- the manifold operations piecewise, so that independent sub-manifolds are handled by different warps concurrently
+// (x [+] d: build_manifold.hpp:188-190; x [-] o with the S2 part of S2.hpp:144-167)
 __device__ __noinline__ void so3_boxminus(const double* xq, const double* oq, double* r) {  // log(o^-1 * x)
   double qc[4] = {-oq[0], -oq[1], -oq[2], oq[3]}, q[4];
   qmul(qc, xq, q);
@@ -257,30 +186,8 @@ __device__ __forceinline__ void pose_from_state(const double* x, PoseDev& p) {
   for (int i = 0; i < 3; ++i) { p.pos[i] = x[i]; p.offT[i] = x[11 + i]; }
 }
 
-// ---- block-cooperative 23x23 helpers on shared memory (row-major, leading dimension NDOF); every thread of the
-// block calls them (they contain __syncthreads)
-// rows [idx, idx+D) of Dst <- J * rows of Src
-template <int D>
-__device__ __forceinline__ void b_mul_rows(double* Dst, const double* Src, int idx, const double* J, int tid) {
-  double t[D];
-  if (tid < NDOF) {
-    for (int i = 0; i < D; ++i) { double s = 0; for (int k = 0; k < D; ++k) s += J[D * i + k] * Src[(idx + k) * NDOF + tid]; t[i] = s; }
-  }
-  __syncthreads();
-  if (tid < NDOF) for (int i = 0; i < D; ++i) Dst[(idx + i) * NDOF + tid] = t[i];
-  __syncthreads();
-}
-template <int D>
-__device__ __forceinline__ void b_mul_cols_T(double* M, int idx, const double* J, int tid) {
-  double t[D];
-  if (tid < NDOF) {
-    for (int j = 0; j < D; ++j) { double s = 0; for (int k = 0; k < D; ++k) s += M[tid * NDOF + idx + k] * J[D * j + k]; t[j] = s; }
-  }
-  __syncthreads();
-  if (tid < NDOF) for (int j = 0; j < D; ++j) M[tid * NDOF + idx + j] = t[j];
-  __syncthreads();
-}
-// ---- the three projected sub-manifolds together.  The projection Jacobian of esekfom.hpp:1665-1703 / :1841-1918 is block
+// ---- block-cooperative 23x23 helpers on shared memory (row-major, leading dimension NDOF); every thread of the block calls
+// them (they contain __syncthreads).  The three projected sub-manifolds together.  The projection Jacobian of esekfom.hpp:1665-1703 / :1841-1918 is block
 // diagonal: identity except J3a on rows/cols 3..5 (rot), J3b on 6..8 (offset_R_L_I) and J2 on 21..22 (grav).  The blocks touch
 // disjoint rows (columns), so all row products form ONE phase and all column products another: 8 x 23 outputs per phase,
 // one per thread, instead of six block-wide phases of 23 busy threads each.  (Entries that sit in the rows of one block and
@@ -321,47 +228,6 @@ __device__ __forceinline__ void b_project(double* M, const double* J3a, const do
   if (tid < PROJ_OUT) M[c * NDOF + q.idx + q.i] = v;
   __syncthreads();
 }
-// Inverse of A (23x23) by Gauss-Jordan with partial pivoting on aug = [A | I] (23 x 46), ping-pong buffered so that one
-// pivot step = ONE barrier: every warp finds the pivot row redundantly (shuffles, first maximum wins), then each
-// thread writes new[r][j] from old values only:  row c <- old[piv]/pivot ;  other rows <- old[src] - old[src][c]*row c
-// (src = c for r == piv: the row swap).  aug must hold 2 * 23 * 46 doubles.  Result -> Ainv.
-__device__ __forceinline__ void b_inverse(const double* A, double* Ainv, double* aug, int tid) {
-  constexpr int W = 2 * NDOF;
-  constexpr int SZ = NDOF * W;
-  const int lane = tid & 31;
-  for (int e = tid; e < SZ; e += ESIKF_THREADS) {
-    const int r = e / W, c = e - r * W;
-    aug[e] = c < NDOF ? A[r * NDOF + c] : ((c - NDOF) == r ? 1.0 : 0.0);
-  }
-  __syncthreads();
-  double* cur = aug;
-  double* nxt = aug + SZ;
-  for (int c = 0; c < NDOF; ++c) {
-    double best = -1.0;
-    int piv = c;
-    if (c + lane < NDOF) { best = fabs(cur[(c + lane) * W + c]); piv = c + lane; }
-    for (int o = 16; o; o >>= 1) {
-      const double ob = __shfl_xor_sync(FULL, best, o);
-      const int op = __shfl_xor_sync(FULL, piv, o);
-      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
-    }
-    const double d = 1.0 / cur[piv * W + c];
-    for (int e = tid; e < SZ; e += ESIKF_THREADS) {
-      const int r = e / W, j = e - r * W;
-      const double pr = cur[piv * W + j] * d;
-      if (r == c) nxt[e] = pr;
-      else {
-        const int src = (r == piv) ? c : r;
-        nxt[e] = cur[src * W + j] - cur[src * W + c] * pr;
-      }
-    }
-    __syncthreads();
-    double* t = cur; cur = nxt; nxt = t;
-  }
-  for (int e = tid; e < NDOF * NDOF; e += ESIKF_THREADS) { const int r = e / NDOF; Ainv[e] = cur[r * W + NDOF + (e - r * NDOF)]; }
-  __syncthreads();
-}
-
 }  // namespace dev
 
 // Load the propagated state / covariance for a new scan.
