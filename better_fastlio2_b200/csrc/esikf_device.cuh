@@ -273,8 +273,10 @@ struct StepResult {
   int passes, searches, lastM, t, need_host, pad_;
   int counters[32];
   int cnt2[2];
-  unsigned long long span_ns;   // device time from the start of k_esikf_begin to this kernel (%globaltimer): the step's own
-                                // GPU time without an event pair on the stream between two steps in flight
+  unsigned long long span_ns;   // device time from the start of k_esikf_begin to the end of the sequence (%globaltimer): the step's
+                                // own GPU time without an event pair on the stream between two steps in flight
+  unsigned long long update_ns; // the same up to k_publish, which starts right behind the last update kernel: the iterated update
+                                // without map_incremental
 };
 __global__ void k_publish(const EsikfCtl* c, const int* __restrict__ counters, const int* __restrict__ cnt2, StepResult* out, int with_tail) {
   pdl_sync();
@@ -282,6 +284,7 @@ __global__ void k_publish(const EsikfCtl* c, const int* __restrict__ counters, c
   for (int i = tid; i < NDOF * NDOF; i += blockDim.x) out->P[i] = c->P[i];
   if (tid < 26) out->x[tid] = c->x[tid];
   if (tid == 64) { out->last_res = c->last_res; out->passes = c->passes; out->searches = c->searches; out->lastM = c->lastM; out->t = c->t; out->need_host = c->need_host; }
+  if (tid == 67) out->update_ns = global_timer_ns() - c->t_begin;
   if (!with_tail) return;   // counters, counts and span: written by the last insert kernel (StepTail, map_kernels.cuh)
   if (tid >= 32 && tid < 64) out->counters[tid - 32] = counters[tid - 32];
   if (tid == 65) { out->cnt2[0] = cnt2 ? cnt2[0] : 0; out->cnt2[1] = cnt2 ? cnt2[1] : 0; }

@@ -1685,6 +1685,7 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
   memset(&r, 0, sizeof(r));
   r.n_deleted = s->step_deleted;
   bool host_path = !s->step_device;
+  float span_ms = 0.f;   // device-driven step: %globaltimer span of the whole sequence
   const int launches0 = m->launches;
   const auto hf0 = std::chrono::steady_clock::now();
   auto hf1 = hf0;
@@ -1704,7 +1705,9 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
       stats_from_ctl(s->h_res, &r.update);
       s->h_cnt2[0] = s->h_res->cnt2[0];
       s->h_cnt2[1] = s->h_res->cnt2[1];
-      r.update.gpu_ms = (float)((double)s->h_res->span_ns * 1e-6);
+      r.update.gpu_ms = (float)((double)s->h_res->update_ns * 1e-6);
+      span_ms = (float)((double)s->h_res->span_ns * 1e-6);
+      if (r.update.gpu_ms > span_ms) r.update.gpu_ms = span_ms;   // (k_publish sits on a parallel branch: never report more than the whole)
     }
   }
   if (host_path) {
@@ -1724,7 +1727,7 @@ extern "C" int flb_scan_step_finish(flb_session* s, flb_fov_state* fov, double* 
   r.n_no_downsample = s->step_n > 0 ? s->h_cnt2[1] : 0;
   r.map_valid = m->h_counters[CNT_VALID];
   if (s->step_ev2) CU(cudaEventElapsedTime(&r.gpu_ms_total, s->ev2, s->ev3));
-  else r.gpu_ms_total = r.update.gpu_ms;
+  else r.gpu_ms_total = span_ms > 0.f ? span_ms : r.update.gpu_ms;
   r.kernel_launches = s->step_l0 + (m->launches - launches0);
   if (out) *out = r;
   const int rrc = maybe_rehash(m);

@@ -178,8 +178,8 @@ int flb_pass_rows(flb_session* s, double* h_x_colmajor, int ld, double* h, int c
 typedef struct flb_update_stats {
   int passes, search_passes, effct_feat_num, converged_count;
   double total_residual;
-  float gpu_ms;            /* device time of all kernels of this update (CUDA events; inside flb_scan_step: the sequence's own
-                              %globaltimer span, update + insert) */
+  float gpu_ms;            /* device time of all kernels of this update (CUDA events; inside flb_scan_step: %globaltimer span from
+                              the sequence's first kernel to just behind its last update kernel) */
 } flb_update_stats;
 
 /* update_iterated_dyn_share_modified (esekfom.hpp:1620-1938) with the built-in measurement model: state26 / P23x23

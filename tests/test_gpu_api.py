@@ -119,6 +119,8 @@ def test_two_sessions_are_independent(oracle):
         t.Build(sc["map"])
         ses = capi.Session(t, max_scan_points=len(sc["body"]), max_iterations=3)
         s, P, r = ses.scan_step(None, sc["body"], sc["prior"], sc["P"], True)
+        # with the scan passed in the call the whole step is bracketed by events; the update times itself on the device
+        assert 0.0 < r.update.gpu_ms <= r.gpu_ms_total < 1e3
         single.append((s, P, sort_rows(t.flatten())))
         ses.close()
         t.close()
@@ -131,6 +133,8 @@ def test_two_sessions_are_independent(oracle):
     outs = [ses.scan_step(None, None, sc["prior"], sc["P"], True) for ses, sc in zip(sess, scs)]
     for (s, P, r), t, ref in zip(outs, trees, single):
         assert np.array_equal(s, ref[0]) and np.array_equal(P, ref[1])
+        # scan already on the device: no event pair around the step, update and whole sequence from the device-side stamps
+        assert 0.0 < r.update.gpu_ms <= r.gpu_ms_total < 1e3
         assert np.array_equal(sort_rows(t.flatten()), ref[2])
     for ses in sess:
         ses.close()
