@@ -9,7 +9,8 @@
 //   ... at shutdown (:2559):  tlog.save(log_path + "fast_lio_time_log.csv");
 //
 // Column mapping: "incremental time" = device time of map_incremental's kernels + the fov delete (gpu_ms_total −
-// update.gpu_ms), "search time" = 0 exactly as in the reference (kdtree_search_time is reset every scan at :2249 and
+// update.gpu_ms; a device-driven step stamps both on the device: the update ends behind its last update kernel, the whole
+// step behind the last insert kernel), "search time" = 0 exactly as in the reference (kdtree_search_time is reset every scan at :2249 and
 // never accumulated), "delete size" = kdtree_delete_counter, "delete time" folded into the incremental column (the
 // delete runs inside the same stream segment), tree sizes = ikdtree.size() before / after, "add point size" =
 // add_point_size (:1494) = n_to_add + n_no_downsample.
